@@ -1,0 +1,73 @@
+"""ctypes binding of include/circkit_b200.h.  There is NO fallback: if the CUDA library is missing or
+cannot be loaded this module raises, and every product entry point fails with it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcirckit_b200.so")
+
+CK_OK = 0
+CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5
+CK_F_NORMALIZE, CK_F_NO_BYTES = 1, 2
+CK_CLASS_2BIT_LE_512, CK_CLASS_2BIT_LE_8192, CK_CLASS_2BIT_LE_65536, CK_CLASS_2BIT_LE_425984 = 1, 2, 4, 8
+
+
+class CkConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch_bytes", C.c_uint64),
+                ("max_batch_records", C.c_uint32), ("table_capacity", C.c_uint64)]
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+_vp, _u64, _u32, _i, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/circkit_b200.h declares
+SIGNATURES = {
+    "ck_init": (_i, [C.POINTER(CkConfig), C.POINTER(_vp)]),
+    "ck_destroy": (None, [_vp]),
+    "ck_last_error": (C.c_char_p, [_vp]),
+    "ck_alloc_pinned": (_vp, [_vp, _sz]),
+    "ck_free_pinned": (None, [_vp, _vp]),
+    "ck_canon_submit": (_i, [_vp, _i, _vp, _vp, _u32, _u32]),
+    "ck_canon_wait": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ck_uniq_submit": (_i, [_vp, _i, _vp, _vp, _u32, _u32, _u64]),
+    "ck_uniq_wait": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "ck_uniq_reset": (_i, [_vp]),
+    "ck_lmsr_index": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "ck_lmsr": (_i, [_vp, _vp, _sz, _vp]),
+    "ck_canonicalize": (_i, [_vp, _vp, _sz, _vp]),
+    "ck_lmsr_index_batch": (_i, [_vp, _vp, _vp, _u32, _vp]),
+    "ck_dev_workspace_bytes": (_u64, [_u32, _u64]),
+    "ck_dev_canon_packed2": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64]),
+    "ck_dev_canon_bytes": (_i, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u64]),
+    "ck_dev_check": (_i, [_vp, _vp, _vp]),
+    "ck_dev_table_bytes": (_u64, [_u64]),
+    "ck_dev_table_clear": (_i, [_vp, _vp, _vp, _u64]),
+    "ck_dev_table_insert": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _vp]),
+    "ck_dev_table_first": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "ck_launch_count": (_u64, [_vp]),
+    "ck_synth_offsets": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _u32, _u32, _u32, _vp, C.POINTER(_u64)]),
+    "ck_synth_packed2": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp]),
+    "ck_dev_unpack2": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -m circkit_b200.build` "
+                "(nvcc, sm_100a).  circkit_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)            # AttributeError if the library lacks a declared symbol
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib

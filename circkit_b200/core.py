@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference's library interface over the C ABI (no compute here).
+
+Reference names kept: ``canonicalize``, ``lmsr``, ``lmsr_index`` (lib/src/canonicalize.rs:5,41,54);
+batch calls correspond to the worker / consumer closures of src/canonicalize.rs:21-44 and
+src/uniq.rs:33-78.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+class CircKitError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"circkit_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One ``ck_ctx``: a device, two in-flight batch slots, the uniq first-occurrence table."""
+
+    def __init__(self, device: int = 0, max_batch_bytes: int = 64 << 20, max_batch_records: int = 1 << 20,
+                 table_capacity: int = 0):
+        self._lib = N.lib()
+        self._h = C.c_void_p()
+        cfg = N.CkConfig(device, max_batch_bytes, max_batch_records, table_capacity)
+        rc = self._lib.ck_init(C.byref(cfg), C.byref(self._h))
+        if rc != N.CK_OK:
+            raise CircKitError(rc, (self._lib.ck_last_error(None) or b"").decode())
+        self.device = device
+        self.max_batch_bytes = max_batch_bytes
+        self.max_batch_records = max_batch_records
+
+    # -- plumbing
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, rc: int):
+        if rc != N.CK_OK:
+            raise CircKitError(rc, (self._lib.ck_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.ck_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        return int(self._lib.ck_launch_count(self._h))
+
+    # -- library drop-ins (library semantics: bytes as they are)
+    def lmsr_index(self, s: bytes) -> int:
+        out = C.c_size_t(0)
+        self._check(self._lib.ck_lmsr_index(self._h, s, len(s), C.byref(out)))
+        return out.value
+
+    def lmsr(self, s: bytes) -> bytes:
+        out = C.create_string_buffer(max(len(s), 1))
+        self._check(self._lib.ck_lmsr(self._h, s, len(s), out))
+        return out.raw[: len(s)]
+
+    def canonicalize(self, s: bytes) -> bytes:
+        out = C.create_string_buffer(max(len(s), 1))
+        self._check(self._lib.ck_canonicalize(self._h, s, len(s), out))
+        return out.raw[: len(s)]
+
+    def lmsr_index_batch(self, arena: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self._lib.ck_lmsr_index_batch(self._h, _ptr(arena), _ptr(offsets), n, _ptr(out)))
+        return out[:n]
+
+    # -- batch API (host buffers)
+    def canon_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool, no_bytes=False):
+        flags = (N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+        self._check(self._lib.ck_canon_submit(self._h, slot, _ptr(arena), _ptr(offsets), len(offsets) - 1, flags))
+
+    def canon_wait(self, slot: int, n: int, total: int, *, want_bytes=True):
+        out = np.zeros(max(total, 1), dtype=np.uint8) if want_bytes else None
+        lens = np.zeros(max(n, 1), dtype=np.uint32)
+        start = np.zeros(max(n, 1), dtype=np.uint32)
+        strand = np.zeros(max(n, 1), dtype=np.uint8)
+        h = np.zeros(max(n, 1), dtype=np.uint64)
+        self._check(self._lib.ck_canon_wait(self._h, slot, _ptr(out), _ptr(lens), _ptr(start), _ptr(strand), _ptr(h)))
+        return dict(out=None if out is None else out[:total], lens=lens[:n], start=start[:n], strand=strand[:n], hash=h[:n])
+
+    def canonicalize_batch(self, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, want_bytes=True):
+        """Worker closure over a batch (src/canonicalize.rs:21-30): returns dict(out, lens, start, strand, hash)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.canon_submit(0, arena, offsets, normalize=normalize, no_bytes=not want_bytes)
+        return self.canon_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes)
+
+    def uniq_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, base_index: int, *, normalize: bool,
+                    no_bytes=False):
+        flags = (N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+        self._check(self._lib.ck_uniq_submit(self._h, slot, _ptr(arena), _ptr(offsets), len(offsets) - 1, flags,
+                                             base_index))
+
+    def uniq_wait(self, slot: int, n: int, total: int, *, want_bytes=True):
+        out = np.zeros(max(total, 1), dtype=np.uint8) if want_bytes else None
+        lens = np.zeros(max(n, 1), dtype=np.uint32)
+        h = np.zeros(max(n, 1), dtype=np.uint64)
+        first = np.zeros(max(n, 1), dtype=np.uint64)
+        self._check(self._lib.ck_uniq_wait(self._h, slot, _ptr(out), _ptr(lens), _ptr(h), _ptr(first)))
+        return dict(out=None if out is None else out[:total], lens=lens[:n], hash=h[:n], first=first[:n])
+
+    def uniq_batch(self, arena: np.ndarray, offsets: np.ndarray, base_index: int = 0, *, normalize: bool = False,
+                   want_bytes=True):
+        """Worker + consumer closures over a batch (src/uniq.rs:33-78): dict(out, lens, hash, first)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.uniq_submit(0, arena, offsets, base_index, normalize=normalize, no_bytes=not want_bytes)
+        return self.uniq_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes)
+
+    def uniq_reset(self):
+        self._check(self._lib.ck_uniq_reset(self._h))
+
+
+_default: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default
+    if _default is None:
+        _default = Context(max_batch_bytes=1 << 20, max_batch_records=1 << 12)
+    return _default
+
+
+def lmsr_index(s: bytes) -> int:
+    """lib/src/canonicalize.rs:5 -- index of the lexicographically minimal rotation (smallest on ties)."""
+    return default_context().lmsr_index(bytes(s))
+
+
+def lmsr(s: bytes) -> bytes:
+    """lib/src/canonicalize.rs:41"""
+    return default_context().lmsr(bytes(s))
+
+
+def canonicalize(s: bytes) -> bytes:
+    """lib/src/canonicalize.rs:54 -- min(lmsr(s), lmsr(revcomp(s))), ties keep the reverse complement."""
+    return default_context().canonicalize(bytes(s))

@@ -1,0 +1,125 @@
+// ck_device.cuh -- device-side building blocks shared by the canonicalize/uniq kernels.
+//
+// Symbol lanes.  A record is a circular string over an ordered alphabet; the kernels work on
+// a packed big-endian image of it so that unsigned integer order == lexicographic order
+// (reference compares unsigned bytes: lib/src/canonicalize.rs:22,25,58):
+//   BITS = 2 : A,C,G,T -> 0..3                       (16 symbols per 32-bit unit)
+//   BITS = 4 : - A B C D G H K M N R S T V W Y -> 0..15  (8 per unit; covers the CLI alphabet
+//              {-,A,C,G,N,T} that needletail::normalize emits and upper-case IUPAC for the lib API)
+//   BITS = 8 : raw bytes                             (4 per unit; any other input, lib semantics)
+// In shared memory a strand is an array X of 32-bit units, unit j holding symbols
+// [j*S, (j+1)*S) MSB-first, extended circularly by >= 64 symbols past n so that a window that
+// starts at any p < n can be read without wrap logic.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+#define CK_FULL 0xffffffffu
+
+namespace ck {
+
+// ------------------------------------------------------------------ constant tables
+// Filled once per process by ck_tables_init() (ck_kernels.cu).
+struct Tables {
+    u8 norm[256];    // needletail 0.5.1 normalize(_, false): 0 = dropped, else mapped byte (src/canonicalize.rs:24)
+    u8 comp[256];    // bio 1.3.1 complement LUT (lib/src/canonicalize.rs:56)
+    u8 code4[256];   // byte -> 4-bit code of the 16-symbol alphabet, 0xFF = not representable
+    u8 sym4[16];     // 4-bit code -> byte
+    u8 comp4[16];    // complement in 4-bit code space
+};
+__constant__ Tables c_tab;   // single translation unit (ck_lib.cu): defined here
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ u32 funnel_l(u32 hi, u32 lo, u32 s)   // top 32 bits of (hi:lo) << s, s in [0,31]
+{
+    return __funnelshift_l(lo, hi, s);
+}
+
+// Reverse-complement of one 32-bit unit of 2-bit symbols (16 bases): reverse the order of the
+// 2-bit groups and complement each (3 - c == ~c on two bits).
+__device__ __forceinline__ u32 revcomp2_u32(u32 x)
+{
+    u32 r = __brev(x);                                            // reverses bits, also inside each pair
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);      // swap the two bits of each pair back
+    return ~r;
+}
+// Same for 4-bit symbols (8 per unit): reverse nibbles, complement through the 16-entry table.
+__device__ __forceinline__ u32 revcomp4_u32(u32 x)
+{
+    u32 r = __byte_perm(x, 0, 0x0123);                            // reverse bytes
+    r = ((r >> 4) & 0x0f0f0f0fu) | ((r & 0x0f0f0f0fu) << 4);      // swap nibbles inside bytes
+    u32 o = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o |= (u32)c_tab.comp4[(r >> (4 * k)) & 15u] << (4 * k);
+    return o;
+}
+__device__ __forceinline__ u32 revcomp8_u32(u32 x)
+{
+    u32 r = __byte_perm(x, 0, 0x0123);
+    u32 o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o |= (u32)c_tab.comp[(r >> (8 * k)) & 255u] << (8 * k);
+    return o;
+}
+template <int BITS> __device__ __forceinline__ u32 revcomp_unit(u32 x)
+{
+    if (BITS == 2) return revcomp2_u32(x);
+    if (BITS == 4) return revcomp4_u32(x);
+    return revcomp8_u32(x);
+}
+
+// ASCII of 4 consecutive 2-bit symbols given as the byte b = c0c1c2c3 (c0 first / most significant):
+// returns a little-endian u32 whose byte k is the letter of c_k.
+__device__ __forceinline__ u32 ascii4_from_2bit(u32 b)
+{
+    // selector nibble k of PRMT picks the output byte k from the "ACGT" table
+    u32 sel = ((b >> 6) & 3u) | (((b >> 4) & 3u) << 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 12);
+    return __byte_perm(0x54474341u /* 'A','C','G','T' */, 0, sel);
+}
+
+// ------------------------------------------------------------------ XXH3-64 (seed 0, default secret)
+// xxhash-rust 0.8.6 xxh3_64 (src/uniq.rs:45), restated from the XXH3 spec.  Secret as LE u64s at
+// byte offsets 8*i is kept in constant memory; unaligned secret reads are composed from it.
+__constant__ __align__(16) u8 c_secret[192 + 8];
+
+__device__ __forceinline__ u64 sec64(int off)        // XXH_readLE64(secret + off), any alignment
+{
+    const u32 *w = reinterpret_cast<const u32 *>(c_secret);
+    int k = off >> 2, s = (off & 3) * 8;
+    u32 a = w[k], b = w[k + 1], c = w[k + 2];
+    u32 lo = s ? __funnelshift_r(a, b, s) : a;
+    u32 hi = s ? __funnelshift_r(b, c, s) : b;
+    return ((u64)hi << 32) | lo;
+}
+#define CK_P32_1 0x9E3779B1ULL
+#define CK_P32_2 0x85EBCA77ULL
+#define CK_P32_3 0xC2B2AE3DULL
+#define CK_P64_1 0x9E3779B185EBCA87ULL
+#define CK_P64_2 0xC2B2AE3D27D4EB4FULL
+#define CK_P64_3 0x165667B19E3779F9ULL
+#define CK_P64_4 0x85EBCA77C2B2AE63ULL
+#define CK_P64_5 0x27D4EB2F165667C5ULL
+#define CK_PMX1 0x165667919E3779F9ULL
+#define CK_PMX2 0x9FB21C651E98DF25ULL
+
+__device__ __forceinline__ u64 mul128_fold64(u64 a, u64 b) { return (a * b) ^ __umul64hi(a, b); }
+__device__ __forceinline__ u64 xxh3_avalanche(u64 h) { h ^= h >> 37; h *= CK_PMX1; h ^= h >> 32; return h; }
+__device__ __forceinline__ u64 xxh64_avalanche(u64 h)
+{
+    h ^= h >> 33; h *= CK_P64_2; h ^= h >> 29; h *= CK_P64_3; h ^= h >> 32; return h;
+}
+__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ u64 bswap64(u64 x)
+{
+    u32 lo = (u32)x, hi = (u32)(x >> 32);
+    return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+
+}  // namespace ck

@@ -1,0 +1,312 @@
+// ck_kernels.cuh -- the kernels of the canonicalize / uniq hot path (sm_100a, no tensor cores:
+// nothing here is a contraction; the work is integer scan + hash + hash-table traffic).
+//
+//   k_prepare      normalise (needletail rules) + classify + pack one batch of raw records
+//   k_classify     route records to a symbol lane / thread shape by alphabet and length
+//   k_canon_warp   warp-per-record LMSR + canonical form + XXH3-64       (viroid / circRNA sizes)
+//   k_canon_cta    CTA-per-record, same algorithm                        (plasmid / mtDNA sizes)
+//   k_table_insert first-occurrence table: CAS the key, atomicMin the input index
+//   k_table_first  read back first_index per record
+#pragma once
+#include "ck_hash.cuh"
+
+namespace ck {
+
+// record classes (index into the per-class work lists)
+enum : int {
+    CLS_W2S = 0,   // 2-bit, warp, n <= 512
+    CLS_W2M = 1,   // 2-bit, warp, n <= 8192
+    CLS_C2A = 2,   // 2-bit, CTA,  n <= 65536
+    CLS_C2B = 3,   // 2-bit, CTA,  n <= 425984
+    CLS_W4 = 4,    // 4-bit, warp, n <= 2048
+    CLS_C4 = 5,    // 4-bit, CTA,  n <= 212992
+    CLS_W8 = 6,    // bytes, warp, n <= 1024
+    CLS_C8 = 7,    // bytes, CTA,  n <= 106496
+    CLS_HUGE = 8,  // anything longer: strands staged in global scratch
+    CLS_EMPTY = 9, // n == 0
+    CLS_COUNT = 10
+};
+__host__ __device__ constexpr u32 cls_max_n(int c)
+{
+    return c == CLS_W2S ? 512u : c == CLS_W2M ? 8192u : c == CLS_C2A ? 65536u : c == CLS_C2B ? 425984u
+         : c == CLS_W4 ? 2048u : c == CLS_C4 ? 212992u : c == CLS_W8 ? 1024u : c == CLS_C8 ? 106496u : 0xffffffffu;
+}
+
+struct CanonArgs {
+    const u64 *packed2;     // 2-bit arena: record i at word (offsets[i] >> 5) + i
+    const u8 *bytes;        // normalised byte arena: record i at offsets[i]
+    const u64 *offsets;     // n_records + 1 symbol offsets
+    const u32 *lens;        // optional normalised lengths (else offsets[i+1] - offsets[i])
+    const u32 *list;        // optional record indices of this class
+    const u32 *count;       // device count of `list` entries (with list), else null
+    u32 n_direct;           // without list: records [0, n_direct)
+    u8 *out;                // canonical ASCII arena (same offsets) or null
+    u32 *out_start;         // or null
+    u8 *out_strand;         // or null
+    u64 *out_hash;          // or null
+    u32 *scratch;           // tie-path scratch, `scratch_stride` u32 per warp (warp shape) / per CTA
+    u64 scratch_stride;
+    u32 smem_units;         // u32 units reserved per strand in (shared) staging memory
+    u32 *xglobal;           // CLS_HUGE only: strands staged here, 2 * smem_units u32 per CTA
+    u32 mode;               // bit0: forward strand only (lmsr / lmsr_index, lib/src/canonicalize.rs:5,41)
+};
+
+// ---------------------------------------------------------------------------------------------
+// canonical ASCII -> global memory in 16-byte destination-aligned chunks (coalesced 128-bit stores;
+// the ragged first/last chunk of a record is written bytewise because neighbours own the rest).
+template <int BITS, typename G>
+__device__ __forceinline__ void emit_ascii(const u32 *X, u32 n, u32 start, u8 *dst)
+{
+    const u32 rank = G::rank(), gs = G::size();
+    const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const u32 nchunks = (n + a + 15u) >> 4;
+    for (u32 c = rank; c < nchunks; c += gs) {
+        const int t0 = (int)(16u * c) - (int)a;
+        u32 tt = t0 < 0 ? (u32)((t0 % (int)n + (int)n) % (int)n) : (u32)t0;   // t0 < n always
+        u32 t8 = tt + 8; if (t8 >= n) t8 %= n;
+        const u64 lo = ascii8<BITS>(X, n, start, tt), hi = ascii8<BITS>(X, n, start, t8);
+        if (t0 >= 0 && (u32)t0 + 16u <= n) {
+            uint4 v = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+            *reinterpret_cast<uint4 *>(dst + t0) = v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int tb = t0 + k;
+                if (tb >= 0 && (u32)tb < n) dst[tb] = (u8)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xffu);
+            }
+        }
+    }
+}
+
+// One record, both shapes.
+template <int BITS, typename G>
+__device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, u32 *Xr, u32 *scr, u64 *hbuf, u32 *red)
+{
+    const u64 off = a.offsets[rec];
+    const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
+    RecordIn in;
+    in.packed2 = a.packed2 ? a.packed2 + ((off >> 5) + rec) : nullptr;
+    in.bytes = a.bytes ? a.bytes + off : nullptr;
+    in.n = n;
+    stage_record<BITS, G>(in, Xf, Xr);
+    RecordOut o = canonical_start<BITS, G>(Xf, Xr, n, scr, red, (a.mode & 1u) != 0);
+    const u32 *X = o.strand ? Xr : Xf;
+    if (a.out) emit_ascii<BITS, G>(X, n, o.start, a.out + off);
+    u64 h = 0;
+    if (a.out_hash) h = xxh3_canonical<BITS, G>(X, n, o.start, hbuf, red);
+    if (G::rank() == 0) {
+        // strand 1 start is reported in forward coordinates: canonical[j] = comp(s[(start - j) mod n])
+        if (a.out_start) a.out_start[rec] = o.strand ? (n - 1 - o.start) : o.start;
+        if (a.out_strand) a.out_strand[rec] = (u8)o.strand;
+        if (a.out_hash) a.out_hash[rec] = h;
+    }
+    G::sync();      // staging memory is reused by the next record
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) k_canon_warp(CanonArgs a)
+{
+    extern __shared__ u32 smem[];
+    typedef Grp<false> G;
+    const u32 wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    u32 *Xf = smem + (size_t)wid * 2 * a.smem_units, *Xr = Xf + a.smem_units;
+    const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
+    u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
+    const u32 count = a.list ? *a.count : a.n_direct;
+    for (u32 e = gw; e < count; e += nw) {
+        const u32 rec = a.list ? a.list[e] : e;
+        do_record<BITS, G>(a, rec, Xf, Xr, scr, nullptr, nullptr);
+    }
+}
+
+template <int BITS, bool XGLOBAL>
+__global__ void __launch_bounds__(1024) k_canon_cta(CanonArgs a)
+{
+    extern __shared__ u32 smem[];
+    __shared__ u32 red[40];
+    __shared__ u64 hbuf[32 * 8];
+    typedef Grp<true> G;
+    u32 *Xf = XGLOBAL ? a.xglobal + (size_t)blockIdx.x * 2 * a.smem_units : smem;
+    u32 *Xr = Xf + a.smem_units;
+    u32 *scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+    const u32 count = a.list ? *a.count : a.n_direct;
+    for (u32 e = blockIdx.x; e < count; e += gridDim.x) {
+        const u32 rec = a.list ? a.list[e] : e;
+        do_record<BITS, G>(a, rec, Xf, Xr, scr, hbuf, red);
+    }
+}
+
+// n == 0 records: canonical form is empty, strand follows the `else` arm, hash is XXH3 of "".
+__global__ void k_canon_empty(CanonArgs a)
+{
+    const u32 count = a.list ? *a.count : a.n_direct;
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const u32 rec = a.list ? a.list[e] : e;
+        if (a.out_start) a.out_start[rec] = 0;
+        if (a.out_strand) a.out_strand[rec] = 1;
+        if (a.out_hash) a.out_hash[rec] = xxh64_avalanche(sec64(56) ^ sec64(64));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_prepare: one warp per raw record.
+//   flags bit0 (normalise): needletail::sequence::normalize(seq, false) -- src/canonicalize.rs:24-27
+//                           (whitespace dropped, acgt -> upper, t/u/U -> T, ./~ -> -, anything else -> N)
+//   otherwise             : library semantics, bytes are taken as they are (lib/src/canonicalize.rs:54)
+// Writes lens[i], lane[i] (2, 4 or 8 bits per symbol) and the record in that lane's format:
+//   lane 2 -> packed2 at word (offsets[i] >> 5) + i;   lanes 4/8 -> normalised bytes at offsets[i].
+struct PrepareArgs {
+    const u8 *raw; const u64 *offsets; u32 n_records; u32 flags;
+    u64 *packed2; u8 *bytes; u32 *lens; u8 *lane;
+};
+__device__ __forceinline__ u32 code2_of(u32 b) { return ((b >> 1) & 3u) ^ ((b >> 2) & 1u); }   // A,C,G,T -> 0..3
+
+__global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
+{
+    const u32 lane = lane_id();
+    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const bool norm = a.flags & 1u;
+    for (u32 rec = gw; rec < a.n_records; rec += nw) {
+        const u64 off = a.offsets[rec];
+        const u32 rawlen = (u32)(a.offsets[rec + 1] - off);
+        const u8 *src = a.raw + off;
+        // pass 1: normalised length and alphabet class
+        u32 cnt = 0, cls = 0;
+        for (u32 base = 0; base < rawlen; base += 32) {
+            u32 t = base + lane;
+            u32 m = 0;
+            if (t < rawlen) { u32 b = __ldg(src + t); m = norm ? (u32)c_tab.norm[b] : (b | 0x100u); }
+            if (m) {
+                u32 b = m & 0xffu;
+                bool acgt = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T');
+                cls |= acgt ? 0u : (c_tab.code4[b] != 0xffu ? 1u : 3u);
+            }
+            cnt += __popc(__ballot_sync(CK_FULL, m != 0));
+        }
+        cls = __reduce_or_sync(CK_FULL, cls);
+        const u32 lanebits = cls == 0 ? 2u : (cls == 1 ? 4u : 8u);
+        if (lane == 0) { a.lens[rec] = cnt; a.lane[rec] = (u8)lanebits; }
+        // pass 2: write in the lane's format
+        u64 *dstw = a.packed2 + ((off >> 5) + rec);
+        u8 *dstb = a.bytes + off;
+        u32 done = 0;                 // normalised symbols written so far
+        u32 acc_hi = 0, acc_lo = 0;   // word under construction (uniform across the warp)
+        for (u32 base = 0; base < rawlen; base += 32) {
+            u32 t = base + lane;
+            u32 m = 0;
+            if (t < rawlen) { u32 b = __ldg(src + t); m = norm ? (u32)c_tab.norm[b] : (b | 0x100u); }
+            const u32 keep = __ballot_sync(CK_FULL, m != 0);
+            const u32 idx = done + __popc(keep & ((1u << lane) - 1u));
+            if (lanebits != 2) {
+                if (m) dstb[idx] = (u8)m;
+            } else {
+                // symbols of this chunk fall into word A = done >> 5 and possibly A + 1
+                const u32 A = done >> 5;
+                u32 c_hi0 = 0, c_lo0 = 0, c_hi1 = 0, c_lo1 = 0;
+                if (m) {
+                    u32 code = code2_of(m & 0xffu), sh = 62 - 2 * (idx & 31u);
+                    u32 hi = sh >= 32 ? code << (sh - 32) : 0u, lo = sh < 32 ? code << sh : 0u;
+                    if ((idx >> 5) == A) { c_hi0 = hi; c_lo0 = lo; } else { c_hi1 = hi; c_lo1 = lo; }
+                }
+                acc_hi |= __reduce_or_sync(CK_FULL, c_hi0);
+                acc_lo |= __reduce_or_sync(CK_FULL, c_lo0);
+                const u32 ndone = done + __popc(keep);
+                if ((ndone >> 5) != A) {          // word A is complete
+                    if (lane == 0) dstw[A] = ((u64)acc_hi << 32) | acc_lo;
+                    acc_hi = __reduce_or_sync(CK_FULL, c_hi1);
+                    acc_lo = __reduce_or_sync(CK_FULL, c_lo1);
+                }
+            }
+            done += __popc(keep);
+        }
+        if (lanebits == 2 && (done & 31u) && lane == 0) dstw[done >> 5] = ((u64)acc_hi << 32) | acc_lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_classify: append every record to the work list of its class (order inside a list is irrelevant:
+// each record writes only its own output slots).
+struct ClassifyArgs {
+    const u64 *offsets; const u32 *lens; const u8 *lane;   // lane == null: every record is 2-bit
+    u32 n_records;
+    u32 *lists;        // CLS_COUNT lists of n_records entries each
+    u32 *counts;       // CLS_COUNT counters (zeroed by the caller)
+};
+__global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1;
+    if (i < a.n_records) {
+        const u32 n = a.lens ? a.lens[i] : (u32)(a.offsets[i + 1] - a.offsets[i]);
+        const u32 bits = a.lane ? a.lane[i] : 2u;
+        if (n == 0) cls = CLS_EMPTY;
+        else if (bits == 2) cls = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M
+                                : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
+        else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
+        else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
+    }
+    // warp-aggregated append, one atomic per (warp, class present)
+    for (int c = 0; c < CLS_COUNT; c++) {
+        const u32 m = __ballot_sync(CK_FULL, cls == c);
+        if (!m) continue;
+        u32 base = 0;
+        const u32 leader = __ffs(m) - 1;
+        if (lane_id() == leader) base = atomicAdd(a.counts + c, __popc(m));
+        base = __shfl_sync(CK_FULL, base, leader);
+        if (cls == c) a.lists[(size_t)c * a.n_records + base + __popc(m & ((1u << lane_id()) - 1u))] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First-occurrence table (replaces HashMap<u64, String, NoHash>, src/uniq.rs:27,47-48,66).
+// slot = {key, first}; key == EMPTY_KEY marks a free slot, and the one real key equal to EMPTY_KEY is
+// kept in a side slot, so every u64 stays a legal XXH3 value.  Keeping the MIN input index per key
+// reproduces "first record seen wins" of the serial consumer for any insertion order.
+struct TableSlot { u64 key; u64 first; };
+#define CK_EMPTY_KEY 0xffffffffffffffffULL
+struct TableArgs {
+    TableSlot *slots; u64 mask;          // capacity - 1 (power of two)
+    u64 *side_first;                     // first index of key == EMPTY_KEY
+    const u64 *hash; const u64 *index;   // index == null: base_index + i
+    u64 base_index; u32 n;
+    u64 *slot_of;                        // out: slot found per record (for k_table_first)
+    u64 *first_out;                      // out (k_table_first)
+    u32 *overflow;                       // set if the table is full
+};
+__device__ __forceinline__ u64 table_home(u64 key, u64 mask) { return (key ^ (key >> 29)) & mask; }
+
+__global__ void __launch_bounds__(256) k_table_insert(TableArgs a)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const u64 key = a.hash[i];
+    const u64 idx = a.index ? a.index[i] : a.base_index + i;
+    if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); a.slot_of[i] = ~0ULL; return; }
+    u64 s = table_home(key, a.mask);
+    for (u64 probes = 0; probes <= a.mask; probes++) {
+        u64 prev = atomicCAS(&a.slots[s].key, CK_EMPTY_KEY, key);
+        if (prev == CK_EMPTY_KEY || prev == key) {
+            atomicMin(&a.slots[s].first, idx);
+            a.slot_of[i] = s;
+            return;
+        }
+        s = (s + 1) & a.mask;
+    }
+    *a.overflow = 1; a.slot_of[i] = ~0ULL - 1;
+}
+__global__ void __launch_bounds__(256) k_table_first(TableArgs a)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const u64 s = a.slot_of[i];
+    a.first_out[i] = s == ~0ULL ? *a.side_first : (s == ~0ULL - 1 ? ~0ULL : a.slots[s].first);
+}
+__global__ void k_table_clear(TableSlot *slots, u64 n, u64 *side_first)
+{
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        slots[i].key = CK_EMPTY_KEY; slots[i].first = ~0ULL;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *side_first = ~0ULL;
+}
+
+}  // namespace ck

@@ -1,0 +1,656 @@
+// ck_lib.cu -- C ABI (include/circkit_b200.h) over the kernels in ck_kernels.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/circkit_b200.h"
+#include "ck_kernels.cuh"
+#include "ck_synth.cuh"
+
+using namespace ck;
+
+namespace {
+
+thread_local std::string g_init_error;
+
+inline const u64 *U(const uint64_t *p) { return reinterpret_cast<const u64 *>(p); }
+inline u64 *U(uint64_t *p) { return reinterpret_cast<u64 *>(p); }
+
+struct ClsCfg { int bits; bool cta; u32 threads; u32 ctas_per_sm; };
+const ClsCfg kCls[CLS_COUNT] = {
+    {2, false, 256, 8},   // CLS_W2S
+    {2, false, 256, 6},   // CLS_W2M
+    {2, true, 512, 4},    // CLS_C2A
+    {2, true, 1024, 1},   // CLS_C2B
+    {4, false, 256, 8},   // CLS_W4
+    {4, true, 1024, 1},   // CLS_C4
+    {8, false, 256, 8},   // CLS_W8
+    {8, true, 1024, 1},   // CLS_C8
+    {0, true, 0, 0},      // CLS_HUGE (handled separately)
+    {0, false, 256, 1},   // CLS_EMPTY
+};
+
+u32 cls_units(int c)
+{
+    const u32 n = cls_max_n(c);
+    switch (kCls[c].bits) {
+    case 2: return strand_units<2>(n);
+    case 4: return strand_units<4>(n);
+    default: return strand_units<8>(n);
+    }
+}
+u64 cls_tie_words(int c)
+{
+    const u64 n = cls_max_n(c);
+    switch (kCls[c].bits) {
+    case 2: return tie_scratch_words<2>(n);
+    case 4: return tie_scratch_words<4>(n);
+    default: return tie_scratch_words<8>(n);
+    }
+}
+u32 cls_smem_bytes(int c)
+{
+    const u32 per = 2u * cls_units(c) * 4u;
+    return kCls[c].cta ? per : per * (kCls[c].threads / 32u);
+}
+
+// One set of tie-path scratch buffers: kernels of one in-flight batch use one set.
+struct ExecScratch {
+    u32 *tie[CLS_COUNT] = {};
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t inserted = nullptr;     // recorded after this slot's table insert
+    u8 *d_raw = nullptr; u64 *d_off = nullptr; u64 *d_p2 = nullptr; u8 *d_norm = nullptr;
+    u32 *d_len = nullptr; u8 *d_lane = nullptr; u8 *d_out = nullptr; u32 *d_start = nullptr;
+    u8 *d_strand = nullptr; u64 *d_hash = nullptr; u64 *d_first = nullptr; u64 *d_slotof = nullptr;
+    u32 *d_lists = nullptr; u32 *d_counts = nullptr;
+    u32 *h_counts = nullptr;            // pinned
+    ExecScratch scr;
+    bool busy = false, uniq = false;
+    u32 n = 0, flags = 0; u64 total = 0;
+};
+
+}  // namespace
+
+struct ck_ctx {
+    int device = 0;
+    int num_sms = 148;
+    ck_config cfg{};
+    std::string err;
+    Slot slot[2];
+    ExecScratch dev_scr;                // device-resident API (one stream at a time)
+    cudaEvent_t last_insert = nullptr;  // insert event of the most recently submitted uniq batch
+    bool have_last_insert = false;
+    TableSlot *table = nullptr; u64 table_slots = 0; u64 *side = nullptr; u32 *d_overflow = nullptr;
+    u64 launches = 0;
+    bool attrs_set = false;
+};
+
+namespace {
+
+int fail(ck_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    std::string m = what;
+    if (e != cudaSuccess) { m += ": "; m += cudaGetErrorString(e); }
+    if (ctx) ctx->err = m; else g_init_error = m;
+    return code;
+}
+#define CK_CUDA(ctx, call)                                                     \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return fail((ctx), CK_ERR_CUDA, #call, e__);   \
+    } while (0)
+
+void fill_tables(Tables &t, u8 secret[200])
+{
+    // needletail 0.5.1 normalize(_, false)
+    for (int c = 0; c < 256; c++) t.norm[c] = 'N';
+    for (const char *p = "ACGTN-"; *p; p++) t.norm[(u8)*p] = (u8)*p;
+    t.norm['a'] = 'A'; t.norm['c'] = 'C'; t.norm['g'] = 'G';
+    t.norm['t'] = 'T'; t.norm['u'] = 'T'; t.norm['U'] = 'T';
+    t.norm['.'] = '-'; t.norm['~'] = '-';
+    t.norm[' '] = 0; t.norm['\t'] = 0; t.norm['\r'] = 0; t.norm['\n'] = 0;
+    // bio 1.3.1 complement
+    for (int c = 0; c < 256; c++) t.comp[c] = (u8)c;
+    const char *a = "AGCTYRWSKMDVHBN", *b = "TCGARYWSMKHBDVN";
+    for (int i = 0; a[i]; i++) { t.comp[(u8)a[i]] = (u8)b[i]; t.comp[(u8)a[i] + 32] = (u8)(b[i] + 32); }
+    // 16-symbol ordered alphabet of the 4-bit lane (closed under complement)
+    const char *alpha = "-ABCDGHKMNRSTVWY";
+    for (int c = 0; c < 256; c++) t.code4[c] = 0xff;
+    for (int i = 0; i < 16; i++) { t.sym4[i] = (u8)alpha[i]; t.code4[(u8)alpha[i]] = (u8)i; }
+    for (int i = 0; i < 16; i++) t.comp4[i] = t.code4[t.comp[t.sym4[i]]];
+    static const u8 sec[192] = {
+        0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+        0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+        0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+        0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+        0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+        0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+        0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+        0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+        0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+        0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+        0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+        0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+    };
+    memset(secret, 0, 200);
+    memcpy(secret, sec, 192);
+}
+
+int alloc_scratch(ck_ctx *ctx, ExecScratch &s)
+{
+    for (int c = 0; c < CLS_COUNT; c++) {
+        if (kCls[c].bits == 0) continue;
+        const u64 groups = (u64)kCls[c].ctas_per_sm * ctx->num_sms * (kCls[c].cta ? 1u : kCls[c].threads / 32u);
+        CK_CUDA(ctx, cudaMalloc(&s.tie[c], groups * cls_tie_words(c) * 4));
+    }
+    return CK_OK;
+}
+void free_scratch(ExecScratch &s)
+{
+    for (int c = 0; c < CLS_COUNT; c++) { if (s.tie[c]) cudaFree(s.tie[c]); s.tie[c] = nullptr; }
+}
+
+template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
+{
+    if (bytes > 48 * 1024) CK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CK_OK;
+}
+int set_attrs(ck_ctx *ctx)
+{
+    if (ctx->attrs_set) return CK_OK;
+    int rc;
+    if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
+    if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
+    if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
+    ctx->attrs_set = true;
+    return CK_OK;
+}
+
+struct CanonIO {
+    const u64 *packed2; const u8 *bytes; const u64 *offsets; const u32 *lens; const u8 *lane;
+    u32 n; u32 mode;
+    u8 *out; u32 *out_start; u8 *out_strand; u64 *out_hash;
+    u32 *lists; u32 *counts;          // CLS_COUNT * n and 16 u32
+};
+
+// classify + one launch per class.  counts[CLS_HUGE] > 0 afterwards means unprocessed records.
+int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io, u32 class_mask)
+{
+    if (io.n == 0) return CK_OK;
+    int rc = set_attrs(ctx);
+    if (rc) return rc;
+    CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 16 * sizeof(u32), st));
+    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts};
+    k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
+    ctx->launches++;
+    for (int c = 0; c < CLS_COUNT; c++) {
+        if (c == CLS_HUGE) continue;
+        if (class_mask && !(class_mask & (1u << c))) continue;
+        CanonArgs a{};
+        a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
+        a.list = io.lists + (size_t)c * io.n; a.count = io.counts + c; a.n_direct = 0;
+        a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
+        a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
+        a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
+        const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
+        const u32 smem = kCls[c].bits ? cls_smem_bytes(c) : 0;
+        switch (c) {
+        case CLS_W2S: case CLS_W2M: k_canon_warp<2><<<grid, thr, smem, st>>>(a); break;
+        case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
+        case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W8: k_canon_warp<8><<<grid, thr, smem, st>>>(a); break;
+        case CLS_C8: k_canon_cta<8, false><<<grid, thr, smem, st>>>(a); break;
+        case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, st>>>(a); break;
+        }
+        ctx->launches++;
+    }
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+
+u64 pow2_at_least(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
+
+int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, u32 *overflow,
+                 const u64 *hash, const u64 *index, u64 base, u32 n, u64 *slot_of)
+{
+    if (!n) return CK_OK;
+    TableArgs t{slots, nslots - 1, side, hash, index, base, n, slot_of, nullptr, overflow};
+    k_table_insert<<<(n + 255) / 256, 256, 0, st>>>(t);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int table_first(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, const u64 *slot_of, u32 n, u64 *first)
+{
+    if (!n) return CK_OK;
+    TableArgs t{slots, nslots - 1, side, nullptr, nullptr, 0, n, const_cast<u64 *>(slot_of), first, nullptr};
+    k_table_first<<<(n + 255) / 256, 256, 0, st>>>(t);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+
+int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                  uint32_t flags, bool uniq, uint64_t base_index)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (slot < 0 || slot > 1) return fail(ctx, CK_ERR_ARG, "slot must be 0 or 1");
+    Slot &s = ctx->slot[slot];
+    if (s.busy) return fail(ctx, CK_ERR_STATE, "slot already holds a batch; call the matching wait first");
+    if (n_records > ctx->cfg.max_batch_records) return fail(ctx, CK_ERR_ARG, "n_records exceeds max_batch_records");
+    if (n_records && (!offsets || (!bytes && offsets[n_records] != offsets[0])))
+        return fail(ctx, CK_ERR_ARG, "null batch pointers");
+    if (uniq && !ctx->table) return fail(ctx, CK_ERR_STATE, "context was created with table_capacity 0");
+    s.n = n_records; s.flags = flags; s.uniq = uniq; s.total = 0;
+    if (n_records == 0) { s.busy = true; return CK_OK; }
+    if (offsets[0] != 0) return fail(ctx, CK_ERR_ARG, "offsets[0] must be 0");
+    const u64 total = offsets[n_records];
+    if (total > ctx->cfg.max_batch_bytes) return fail(ctx, CK_ERR_ARG, "batch exceeds max_batch_bytes");
+    for (u32 i = 0; i < n_records; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, CK_ERR_ARG, "offsets must be non-decreasing");
+        if (offsets[i + 1] - offsets[i] > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+    }
+    s.total = total;
+    cudaStream_t st = s.stream;
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
+    PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
+    k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
+    ctx->launches++;
+    CanonIO io{};
+    io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = s.d_len; io.lane = s.d_lane;
+    io.n = n_records; io.mode = 0;
+    io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
+    io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
+    io.lists = s.d_lists; io.counts = s.d_counts;
+    int rc = run_canon(ctx, st, s.scr, io, 0);
+    if (rc) return rc;
+    if (uniq) {
+        rc = table_insert(ctx, st, ctx->table, ctx->table_slots, ctx->side, ctx->d_overflow, s.d_hash, nullptr,
+                          base_index, n_records, s.d_slotof);
+        if (rc) return rc;
+        CK_CUDA(ctx, cudaEventRecord(s.inserted, st));
+        // first_index of this batch may point into the previous batch: wait for that batch's insert
+        if (ctx->have_last_insert && ctx->last_insert != s.inserted) CK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->last_insert, 0));
+        ctx->last_insert = s.inserted; ctx->have_last_insert = true;
+        rc = table_first(ctx, st, ctx->table, ctx->table_slots, ctx->side, s.d_slotof, n_records, s.d_first);
+        if (rc) return rc;
+        CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts + 16, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts, s.d_counts, 16 * 4, cudaMemcpyDeviceToHost, st));
+    s.busy = true;
+    return CK_OK;
+}
+
+int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start,
+                uint8_t *out_strand, uint64_t *out_hash, uint64_t *out_first)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (slot < 0 || slot > 1) return fail(ctx, CK_ERR_ARG, "slot must be 0 or 1");
+    Slot &s = ctx->slot[slot];
+    if (!s.busy || s.uniq != uniq) return fail(ctx, CK_ERR_STATE, "no matching submit on this slot");
+    s.busy = false;
+    if (s.n == 0) return CK_OK;
+    cudaStream_t st = s.stream;
+    const size_t n = s.n;
+    if (out_bytes && !(s.flags & CK_F_NO_BYTES) && s.total)
+        CK_CUDA(ctx, cudaMemcpyAsync(out_bytes, s.d_out, s.total, cudaMemcpyDeviceToHost, st));
+    if (out_len) CK_CUDA(ctx, cudaMemcpyAsync(out_len, s.d_len, n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_start) CK_CUDA(ctx, cudaMemcpyAsync(out_start, s.d_start, n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_strand) CK_CUDA(ctx, cudaMemcpyAsync(out_strand, s.d_strand, n, cudaMemcpyDeviceToHost, st));
+    if (out_hash) CK_CUDA(ctx, cudaMemcpyAsync(out_hash, s.d_hash, n * 8, cudaMemcpyDeviceToHost, st));
+    if (out_first && uniq) CK_CUDA(ctx, cudaMemcpyAsync(out_first, s.d_first, n * 8, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (s.h_counts[CLS_HUGE]) return fail(ctx, CK_ERR_TOO_LONG, "batch holds a record beyond the staged-length classes");
+    if (uniq && s.h_counts[16]) return fail(ctx, CK_ERR_TABLE_FULL, "uniq table is full; raise table_capacity");
+    return CK_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int ck_init(const ck_config *cfg, ck_ctx **out)
+{
+    if (!cfg || !out) return fail(nullptr, CK_ERR_ARG, "null argument");
+    *out = nullptr;
+    ck_ctx *ctx = new (std::nothrow) ck_ctx();
+    if (!ctx) return fail(nullptr, CK_ERR_ARG, "out of host memory");
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+#define CK_INIT(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) { fail(nullptr, CK_ERR_CUDA, #call, e__); ck_destroy(ctx); return CK_ERR_CUDA; } \
+    } while (0)
+    CK_INIT(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK_INIT(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->num_sms = prop.multiProcessorCount;
+    Tables t; u8 secret[200];
+    fill_tables(t, secret);
+    CK_INIT(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+    CK_INIT(cudaMemcpyToSymbol(c_secret, secret, sizeof(secret)));
+    if (alloc_scratch(ctx, ctx->dev_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
+    const u64 B = cfg->max_batch_bytes, R = cfg->max_batch_records;
+    if (B || R) {
+        for (int k = 0; k < 2; k++) {
+            Slot &s = ctx->slot[k];
+            CK_INIT(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CK_INIT(cudaEventCreateWithFlags(&s.inserted, cudaEventDisableTiming));
+            CK_INIT(cudaMalloc(&s.d_raw, B + 16));
+            CK_INIT(cudaMalloc(&s.d_norm, B + 16));
+            CK_INIT(cudaMalloc(&s.d_out, B + 16));
+            CK_INIT(cudaMalloc(&s.d_p2, (B / 32 + R + 2) * 8));
+            CK_INIT(cudaMalloc(&s.d_off, (R + 1) * 8));
+            CK_INIT(cudaMalloc(&s.d_len, (R + 1) * 4));
+            CK_INIT(cudaMalloc(&s.d_lane, R + 1));
+            CK_INIT(cudaMalloc(&s.d_start, (R + 1) * 4));
+            CK_INIT(cudaMalloc(&s.d_strand, R + 1));
+            CK_INIT(cudaMalloc(&s.d_hash, (R + 1) * 8));
+            CK_INIT(cudaMalloc(&s.d_first, (R + 1) * 8));
+            CK_INIT(cudaMalloc(&s.d_slotof, (R + 1) * 8));
+            CK_INIT(cudaMalloc(&s.d_lists, (size_t)CLS_COUNT * (R + 1) * 4));
+            CK_INIT(cudaMalloc(&s.d_counts, 16 * 4));
+            CK_INIT(cudaMallocHost(&s.h_counts, 32 * 4));
+            memset(s.h_counts, 0, 32 * 4);
+            if (alloc_scratch(ctx, s.scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
+        }
+    }
+    CK_INIT(cudaMalloc(&ctx->side, 8));
+    CK_INIT(cudaMalloc(&ctx->d_overflow, 4));
+    CK_INIT(cudaMemset(ctx->d_overflow, 0, 4));
+    if (cfg->table_capacity) {
+        ctx->table_slots = pow2_at_least(2 * cfg->table_capacity + 16);
+        CK_INIT(cudaMalloc(&ctx->table, ctx->table_slots * sizeof(TableSlot)));
+        k_table_clear<<<ctx->num_sms * 4, 256>>>(ctx->table, ctx->table_slots, ctx->side);
+        CK_INIT(cudaGetLastError());
+    }
+    CK_INIT(cudaDeviceSynchronize());
+#undef CK_INIT
+    *out = ctx;
+    return CK_OK;
+}
+
+void ck_destroy(ck_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < 2; k++) {
+        Slot &s = ctx->slot[k];
+        void *ptrs[] = {s.d_raw, s.d_off, s.d_p2, s.d_norm, s.d_len, s.d_lane, s.d_out, s.d_start, s.d_strand,
+                        s.d_hash, s.d_first, s.d_slotof, s.d_lists, s.d_counts};
+        for (void *p : ptrs) if (p) cudaFree(p);
+        if (s.h_counts) cudaFreeHost(s.h_counts);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.inserted) cudaEventDestroy(s.inserted);
+        free_scratch(s.scr);
+    }
+    free_scratch(ctx->dev_scr);
+    if (ctx->table) cudaFree(ctx->table);
+    if (ctx->side) cudaFree(ctx->side);
+    if (ctx->d_overflow) cudaFree(ctx->d_overflow);
+    delete ctx;
+}
+
+const char *ck_last_error(const ck_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+void *ck_alloc_pinned(ck_ctx *ctx, size_t bytes)
+{
+    void *p = nullptr;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { if (ctx) ctx->err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void ck_free_pinned(ck_ctx *, void *p) { if (p) cudaFreeHost(p); }
+
+int ck_canon_submit(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records, uint32_t flags)
+{
+    return submit_common(ctx, slot, bytes, offsets, n_records, flags, false, 0);
+}
+int ck_canon_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start,
+                  uint8_t *out_strand, uint64_t *out_hash64)
+{
+    return wait_common(ctx, slot, false, out_bytes, out_len, out_start, out_strand, out_hash64, nullptr);
+}
+int ck_uniq_submit(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                   uint32_t flags, uint64_t base_index)
+{
+    return submit_common(ctx, slot, bytes, offsets, n_records, flags, true, base_index);
+}
+int ck_uniq_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, uint64_t *out_hash64, uint64_t *out_first_index)
+{
+    return wait_common(ctx, slot, true, out_bytes, out_len, nullptr, nullptr, out_hash64, out_first_index);
+}
+int ck_uniq_reset(ck_ctx *ctx)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (!ctx->table) return CK_OK;
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CK_CUDA(ctx, cudaDeviceSynchronize());
+    k_table_clear<<<ctx->num_sms * 4, 256>>>(ctx->table, ctx->table_slots, ctx->side);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaMemset(ctx->d_overflow, 0, 4));
+    CK_CUDA(ctx, cudaDeviceSynchronize());
+    ctx->have_last_insert = false;
+    return CK_OK;
+}
+
+// ---- single-record / library-semantics entry points -------------------------------------------
+static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records, u32 mode,
+                     uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand)
+{
+    if (!ctx || !offsets) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
+    if (n_records == 0) return CK_OK;
+    const u64 total = offsets[n_records];
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    u8 *d_raw = nullptr, *d_norm = nullptr, *d_out = nullptr, *d_lane = nullptr, *d_strand = nullptr;
+    u64 *d_off = nullptr, *d_p2 = nullptr; u32 *d_len = nullptr, *d_start = nullptr, *d_lists = nullptr, *d_counts = nullptr;
+    const size_t R = n_records;
+    int rc = CK_OK;
+    u32 h_counts[16] = {};
+    cudaError_t e = cudaSuccess;
+#define CK_LB(call) do { if (e == cudaSuccess) e = (call); } while (0)
+    CK_LB(cudaMalloc(&d_raw, total + 16)); CK_LB(cudaMalloc(&d_norm, total + 16)); CK_LB(cudaMalloc(&d_out, total + 16));
+    CK_LB(cudaMalloc(&d_p2, (total / 32 + R + 2) * 8)); CK_LB(cudaMalloc(&d_off, (R + 1) * 8));
+    CK_LB(cudaMalloc(&d_len, R * 4)); CK_LB(cudaMalloc(&d_lane, R)); CK_LB(cudaMalloc(&d_start, R * 4));
+    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, (size_t)CLS_COUNT * R * 4)); CK_LB(cudaMalloc(&d_counts, 64));
+    CK_LB(cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice));
+    if (total) CK_LB(cudaMemcpy(d_raw, bytes, total, cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) {
+        PrepareArgs pa{d_raw, d_off, n_records, 0u, d_p2, d_norm, d_len, d_lane};
+        k_prepare<<<ctx->num_sms * 8, 256>>>(pa);
+        ctx->launches++;
+        CanonIO io{};
+        io.packed2 = d_p2; io.bytes = d_norm; io.offsets = d_off; io.lens = d_len; io.lane = d_lane; io.n = n_records;
+        io.mode = mode; io.out = out_bytes ? d_out : nullptr; io.out_start = d_start; io.out_strand = d_strand;
+        io.out_hash = nullptr; io.lists = d_lists; io.counts = d_counts;
+        rc = run_canon(ctx, 0, ctx->dev_scr, io, 0);
+    }
+    if (rc == CK_OK) {
+        CK_LB(cudaMemcpy(h_counts, d_counts, 64, cudaMemcpyDeviceToHost));
+        if (out_bytes && total) CK_LB(cudaMemcpy(out_bytes, d_out, total, cudaMemcpyDeviceToHost));
+        if (out_start) CK_LB(cudaMemcpy(out_start, d_start, R * 4, cudaMemcpyDeviceToHost));
+        if (out_strand) CK_LB(cudaMemcpy(out_strand, d_strand, R, cudaMemcpyDeviceToHost));
+    }
+#undef CK_LB
+    void *ptrs[] = {d_raw, d_norm, d_out, d_p2, d_off, d_len, d_lane, d_start, d_strand, d_lists, d_counts};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, CK_ERR_CUDA, "library-semantics batch", e);
+    if (h_counts[CLS_HUGE]) return fail(ctx, CK_ERR_TOO_LONG, "record beyond the staged-length classes");
+    return CK_OK;
+}
+
+int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records, uint32_t *out_index)
+{
+    return lib_batch(ctx, bytes, offsets, n_records, 1u, nullptr, out_index, nullptr);
+}
+int ck_lmsr_index(ck_ctx *ctx, const uint8_t *s, size_t n, size_t *out_index)
+{
+    if (!out_index) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
+    if (n > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+    uint64_t off[2] = {0, (uint64_t)n};
+    uint32_t idx = 0;
+    int rc = lib_batch(ctx, s, off, 1, 1u, nullptr, &idx, nullptr);
+    *out_index = idx;
+    return rc;
+}
+int ck_lmsr(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out)
+{
+    if (n > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+    uint64_t off[2] = {0, (uint64_t)n};
+    return lib_batch(ctx, s, off, 1, 1u, out, nullptr, nullptr);
+}
+int ck_canonicalize(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out)
+{
+    if (n > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+    uint64_t off[2] = {0, (uint64_t)n};
+    return lib_batch(ctx, s, off, 1, 0u, out, nullptr, nullptr);
+}
+
+// ---- device-resident API ---------------------------------------------------------------------
+uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
+{
+    u64 b = 256 + (u64)CLS_COUNT * 4 * ((u64)n_records + 1);
+    if (total_bytes) b += (total_bytes / 32 + n_records + 2) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
+    return (b + 255) & ~255ull;
+}
+int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records,
+                         uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand,
+                         uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (workspace_bytes < ck_dev_workspace_bytes(n_records, 0)) return fail(ctx, CK_ERR_ARG, "workspace too small");
+    CanonIO io{};
+    io.packed2 = U(packed2); io.offsets = U(offsets); io.n = n_records;
+    io.out = out_bytes; io.out_start = out_start; io.out_strand = out_strand; io.out_hash = U(out_hash64);
+    io.counts = (u32 *)workspace; io.lists = (u32 *)((u8 *)workspace + 256);
+    return run_canon(ctx, (cudaStream_t)stream, ctx->dev_scr, io, class_mask);
+}
+int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                       uint64_t total_bytes, uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_len,
+                       uint32_t *out_start, uint8_t *out_strand, uint64_t *out_hash64, void *workspace,
+                       uint64_t workspace_bytes)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (!out_len) return fail(ctx, CK_ERR_ARG, "out_len is required");
+    if (!total_bytes || workspace_bytes < ck_dev_workspace_bytes(n_records, total_bytes))
+        return fail(ctx, CK_ERR_ARG, "workspace too small");
+    if (!n_records) return CK_OK;
+    u8 *w = (u8 *)workspace;
+    u32 *counts = (u32 *)w; w += 256;
+    u32 *lists = (u32 *)w; w += (u64)CLS_COUNT * 4 * ((u64)n_records + 1);
+    u64 *p2 = (u64 *)w; w += (total_bytes / 32 + n_records + 2) * 8;
+    u8 *norm = w; w += (total_bytes + 63) & ~63ull;
+    u8 *lane = w;
+    cudaStream_t st = (cudaStream_t)stream;
+    PrepareArgs pa{bytes, U(offsets), n_records, flags & CK_F_NORMALIZE, p2, norm, out_len, lane};
+    k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
+    ctx->launches++;
+    CanonIO io{};
+    io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
+    io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand;
+    io.out_hash = U(out_hash64); io.counts = counts; io.lists = lists;
+    return run_canon(ctx, st, ctx->dev_scr, io, class_mask);
+}
+int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace)
+{
+    if (!ctx) return CK_ERR_ARG;
+    u32 h[16];
+    CK_CUDA(ctx, cudaMemcpyAsync(h, workspace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (h[CLS_HUGE]) return fail(ctx, CK_ERR_TOO_LONG, "batch holds a record beyond the staged-length classes");
+    return CK_OK;
+}
+
+uint64_t ck_dev_table_bytes(uint64_t capacity_keys) { return pow2_at_least(2 * capacity_keys + 16) * sizeof(TableSlot) + 64; }
+static bool table_view(void *table, u64 bytes, TableSlot *&slots, u64 &nslots, u64 *&side, u32 *&overflow)
+{
+    if (!table || bytes < 64 + sizeof(TableSlot) * 16) return false;
+    nslots = 1; while (nslots * 2 * sizeof(TableSlot) + 64 <= bytes) nslots <<= 1;
+    side = (u64 *)table; overflow = (u32 *)((u8 *)table + 8);
+    slots = (TableSlot *)((u8 *)table + 64);
+    return true;
+}
+int ck_dev_table_clear(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes)
+{
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
+    CK_CUDA(ctx, cudaMemsetAsync(table, 0, 64, (cudaStream_t)stream));
+    k_table_clear<<<ctx->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(slots, nslots, side);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_table_insert(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *hash64,
+                        const uint64_t *index, uint64_t base_index, uint32_t n, uint64_t *slot_scratch)
+{
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
+    return table_insert(ctx, (cudaStream_t)stream, slots, nslots, side, ov, U(hash64), U(index), base_index, n, U(slot_scratch));
+}
+int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *slot_scratch,
+                       uint32_t n, uint64_t *out_first_index)
+{
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
+    return table_first(ctx, (cudaStream_t)stream, slots, nslots, side, U(slot_scratch), n, U(out_first_index));
+}
+uint64_t ck_launch_count(const ck_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- synthetic workloads -------------------------------------------------------------------
+int ck_synth_offsets(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records, uint32_t kind,
+                     uint32_t lo, uint32_t hi, uint32_t dup_permille, uint64_t *offsets_dev, uint64_t *total_out_host)
+{
+    if (!ctx || !offsets_dev || lo < 1 || hi < lo) return ctx ? fail(ctx, CK_ERR_ARG, "bad synth arguments") : CK_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    u64 *lens = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+    CK_CUDA(ctx, cudaMalloc(&lens, ((size_t)n_records + 1) * 8));
+    CK_CUDA(ctx, cudaMemsetAsync(lens, 0, ((size_t)n_records + 1) * 8, st));
+    SynthArgs a{seed, n_records, kind, lo, hi, dup_permille, 0, first_index};
+    if (n_records) k_synth_lens<<<(n_records + 255) / 256, 256, 0, st>>>(a, lens);
+    ctx->launches++;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, U(offsets_dev), (int)n_records + 1, st);
+    CK_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 8));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lens, U(offsets_dev), (int)n_records + 1, st);
+    ctx->launches++;
+    u64 total = 0;
+    CK_CUDA(ctx, cudaMemcpyAsync(&total, offsets_dev + n_records, 8, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(lens); cudaFree(tmp);
+    if (total_out_host) *total_out_host = total;
+    return CK_OK;
+}
+int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
+                     const uint64_t *offsets_dev, uint32_t dup_permille, uint32_t adversarial_permille, uint64_t *packed2_dev)
+{
+    if (!ctx || !offsets_dev || !packed2_dev) return ctx ? fail(ctx, CK_ERR_ARG, "bad synth arguments") : CK_ERR_ARG;
+    SynthArgs a{seed, n_records, 0, 0, 0, dup_permille, adversarial_permille, first_index};
+    if (n_records) k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev));
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_unpack2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records, uint8_t *ascii_out)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (n_records) k_unpack2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(U(packed2), U(offsets), n_records, ascii_out);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+
+}  // extern "C"

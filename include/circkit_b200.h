@@ -1,0 +1,145 @@
+/*
+ * circkit_b200.h -- C ABI of the B200 (sm_100a) canonicalize / uniq hot path of circKit.
+ *
+ * The reference (Benjamin-Lee/circkit, pure Rust) has no FFI of its own; the seam this library
+ * replaces is the pair of closures that `seq_io::parallel::parallel_fasta` drives:
+ *
+ *   worker closure    src/canonicalize.rs:21-30, src/uniq.rs:33-41
+ *                     needletail::sequence::normalize(record.seq(), false) -> circkit::canonicalize(..)
+ *   consumer closure  src/uniq.rs:42-78
+ *                     xxh3_64(canonical) -> HashMap<u64,String> first-occurrence probe
+ *
+ * and the library entry points lib/src/canonicalize.rs:5 (lmsr_index), :41 (lmsr), :54 (canonicalize).
+ * A `circkit-cuda` crate binds exactly these symbols (see INTEGRATION.md for the Rust side).
+ *
+ * Conventions
+ *   - every function returns CK_OK (0) or a negative CK_ERR_* code; ck_last_error() gives the text;
+ *     nothing is printed, no exception crosses the ABI (the reference is silent on success:
+ *     tests/canon_uniq.rs:74-77);
+ *   - the caller owns every buffer; the library keeps no caller pointer past the matching *_wait;
+ *   - a batch is `bytes` (concatenated record.seq() bytes) + `offsets[n_records + 1]`; outputs use the
+ *     SAME offsets: record i's canonical bytes are out_bytes[offsets[i] .. offsets[i] + out_len[i]);
+ *   - one producer thread per context; `slot` (0 or 1) selects one of two in-flight batches, each with
+ *     its own CUDA stream and device staging, so copy-in, kernels and copy-out of consecutive batches
+ *     overlap (the replacement for parallel_fasta's queue of 64 record sets).
+ */
+#ifndef CIRCKIT_B200_H
+#define CIRCKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CK_OK 0
+#define CK_ERR_CUDA (-1)       /* a CUDA runtime call failed (no device, out of memory, ...) */
+#define CK_ERR_ARG (-2)        /* bad argument */
+#define CK_ERR_STATE (-3)      /* wait without submit, slot busy, ... */
+#define CK_ERR_TOO_LONG (-4)   /* a record exceeds the supported length (2^30 symbols) */
+#define CK_ERR_TABLE_FULL (-5) /* first-occurrence table capacity exhausted */
+
+/* flags of ck_canon_submit / ck_uniq_submit */
+#define CK_F_NORMALIZE 1u   /* apply needletail::sequence::normalize(seq, false) first (CLI semantics,
+                               src/canonicalize.rs:24-27); without it bytes are used as they are, like
+                               circkit::canonicalize (lib/src/canonicalize.rs:54) */
+#define CK_F_NO_BYTES 2u    /* do not produce canonical bytes (start/strand/hash only) */
+
+typedef struct ck_ctx ck_ctx;
+
+typedef struct ck_config {
+    int32_t device;            /* CUDA device ordinal */
+    uint64_t max_batch_bytes;  /* largest `bytes` a batch may carry (staging is sized once) */
+    uint32_t max_batch_records;
+    uint64_t table_capacity;   /* distinct canonical forms the uniq table must hold (0: uniq unused) */
+} ck_config;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int ck_init(const ck_config *cfg, ck_ctx **out);
+void ck_destroy(ck_ctx *ctx);
+const char *ck_last_error(const ck_ctx *ctx);   /* ctx may be NULL: error of a failed ck_init */
+void *ck_alloc_pinned(ck_ctx *ctx, size_t bytes);
+void ck_free_pinned(ck_ctx *ctx, void *p);
+
+/* ---- batch API: the worker closure (normalise + canonicalise) ------------------------------- */
+int ck_canon_submit(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets,
+                    uint32_t n_records, uint32_t flags);
+/* any out pointer may be NULL.  out_start/out_strand: canonical[j] = s[(start + j) mod n] when strand
+ * is 0, complement(s[(start - j) mod n]) when 1 (s = the normalised record).  out_hash64 = XXH3-64. */
+int ck_canon_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start,
+                  uint8_t *out_strand, uint64_t *out_hash64);
+
+/* ---- batch API: worker + consumer closure (uniq) --------------------------------------------
+ * base_index = input-order index of the batch's first record.  out_first_index[i] = index of the first
+ * record (over everything submitted to this context so far) whose canonical form has record i's hash;
+ * record i is written by `circkit uniq` iff out_first_index[i] == base_index + i, otherwise it is the
+ * `duplicate_id` row of out_first_index[i] in --table (src/uniq.rs:47-71). */
+int ck_uniq_submit(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets,
+                   uint32_t n_records, uint32_t flags, uint64_t base_index);
+int ck_uniq_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, uint64_t *out_hash64,
+                 uint64_t *out_first_index);
+int ck_uniq_reset(ck_ctx *ctx);   /* forget every key (new input file) */
+
+/* ---- library drop-ins (single record, library semantics: no normalisation) -------------------
+ * lib/src/canonicalize.rs:5,41,54.  These run the same device kernels on a batch of one. */
+int ck_lmsr_index(ck_ctx *ctx, const uint8_t *s, size_t n, size_t *out_index);
+int ck_lmsr(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out);
+int ck_canonicalize(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out);
+/* batched forms of the same three (library semantics), for callers that hold many records */
+int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                        uint32_t *out_index);
+
+/* ---- device-resident API (buffers already in HBM; used by bench.py and the multi-GPU driver) --
+ * All pointers are device pointers, `stream` is a cudaStream_t (0 = default stream).  Nothing is copied
+ * and nothing synchronises; call ck_dev_check() once a stream's work matters.
+ * packed2: 2-bit arena, A,C,G,T = 0..3, 32 bases per u64, first base in the top bits; record i starts at
+ * word (offsets[i] >> 5) + i.  class_mask: 0 = any record; else a promise about the batch (bit c set =
+ * length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
+ * records outside the promise are reported by ck_dev_check(), never silently dropped. */
+#define CK_CLASS_2BIT_LE_512 (1u << 0)
+#define CK_CLASS_2BIT_LE_8192 (1u << 1)
+#define CK_CLASS_2BIT_LE_65536 (1u << 2)
+#define CK_CLASS_2BIT_LE_425984 (1u << 3)
+uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes /* 0 for the packed2 entry */);
+int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets,
+                         uint32_t n_records, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start,
+                         uint8_t *out_strand, uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
+/* raw/normalised bytes -> lane formats (the k_prepare step), then canonicalise; out_len is required */
+int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets,
+                       uint32_t n_records, uint64_t total_bytes, uint32_t flags, uint32_t class_mask,
+                       uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start, uint8_t *out_strand,
+                       uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
+/* synchronises `stream`; CK_ERR_TOO_LONG if the last call on `workspace` left records unprocessed */
+int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace);
+/* first-occurrence table over device arrays; index == NULL means base_index + i */
+uint64_t ck_dev_table_bytes(uint64_t capacity_keys);
+int ck_dev_table_clear(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes);
+int ck_dev_table_insert(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *hash64,
+                        const uint64_t *index, uint64_t base_index, uint32_t n, uint64_t *slot_scratch);
+int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *slot_scratch,
+                       uint32_t n, uint64_t *out_first_index);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t ck_launch_count(const ck_ctx *ctx);
+
+/* ---- synthetic workloads of BASELINE.json (device generators, bench + tests) ------------------
+ * Record g = first_index + i is a pure function of (seed, g): any shard can be generated on any rank.
+ * lengths: kind 0 = uniform integer [lo, hi], 1 = log-uniform [lo, hi]; dup_permille/1000 of the records
+ * are duplicates (random rotation, reverse complement w.p. 1/2) of an earlier original and share its
+ * length.  Writes n_records + 1 offsets; synchronises `stream` to return the total. */
+int ck_synth_offsets(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
+                     uint32_t kind, uint32_t lo, uint32_t hi, uint32_t dup_permille, uint64_t *offsets_dev,
+                     uint64_t *total_out_host);
+/* content in the packed2 layout; adversarial_permille/1000 of the originals are tandem repeats
+ * (period 1, 2, 3, 7, 171, n/2) or carry >= 1 kb poly-A runs (config 4) */
+int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
+                     const uint64_t *offsets_dev, uint32_t dup_permille, uint32_t adversarial_permille,
+                     uint64_t *packed2_dev);
+/* 2-bit arena -> ASCII arena (record i at offsets[i]) */
+int ck_dev_unpack2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records,
+                   uint8_t *ascii_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIRCKIT_B200_H */
