@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- canonicalize+uniq throughput of the B200 hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port of circKit's path)
+
+A step = one pass of the hot path over one batch of synthetic records:
+  config 2 of BASELINE.json (default): `circkit uniq` on 10 M circRNA-length records (log-uniform
+  0.2-5 kb, 30 % duplicates as random rotations / reverse complements), per GPU (weak scaling);
+  the batch is resident in HBM as a packed 2-bit arena when the timed region starts (`value`);
+  `e2e` runs the same records through the host-buffer C ABI (ck_uniq_submit / ck_uniq_wait) from pinned
+  host memory, copies included.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (records per GPU, length law, lo, hi, dup permille, adversarial permille, uniq?, class mask)
+    "c1": dict(records=1_000_000, kind=0, lo=250, hi=400, dup=0, adv=0, uniq=False, mask=1,
+               desc="config 1: canonicalize, 1M viroid-length (250-400 nt) records"),
+    "c2": dict(records=10_000_000, kind=1, lo=200, hi=5000, dup=300, adv=0, uniq=True, mask=1 | 2,
+               desc="config 2: uniq, 10M circRNA-length (0.2-5 kb log-uniform) records, 30% rotated/revcomp duplicates"),
+    "c4": dict(records=200_000, kind=1, lo=5000, hi=200_000, dup=0, adv=10, uniq=False, mask=2 | 4 | 8,
+               desc="config 4: canonicalize, 200k plasmid/mtDNA-length (5-200 kb) records, 1% adversarial repeats"),
+    "c5": dict(records=12_500_000, kind=0, lo=250, hi=400, dup=300, adv=0, uniq=True, mask=1,
+               desc="config 5: uniq, 100M viroid-length records over 8 GPUs (12.5M per GPU), 30% duplicates"),
+}
+SEEDS = {"c1": 1, "c2": 2, "c4": 4, "c5": 5}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline measurement")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # median over the samples taken under load (upper half of the clock samples)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(w, seed, cpu_seconds, steps, warmup, uniq):
+    """circKit's CPU path (oracle port, O(1)-indexed Duval) on a bounded sample of the workload.
+
+    Worker stage (normalise + canonicalize, src/uniq.rs:33-41) on all host cores; consumer stage
+    (xxh3 + first-occurrence map, src/uniq.rs:42-78) single-threaded as in the reference.  The two
+    overlap in the reference (parallel_fasta pipelines them), so a step's time is max(worker, consumer)."""
+    import numpy as np
+    import oracle
+    from oracle import synth
+    cores = oracle.max_threads()
+    pilot_n = 2000
+    a, o = synth.make_records(pilot_n, w["kind"], w["lo"], w["hi"], w["dup"], seed)
+    t = time.perf_counter()
+    oracle.canonicalize_batch(a, o, normalize=True, threads=cores, want_start=False, want_hash=False)
+    rate = pilot_n / max(time.perf_counter() - t, 1e-6)
+    per_step = max(cpu_seconds / max(steps + warmup, 1), 0.5)
+    n = int(min(max(rate * per_step, 2000), 2_000_000))
+    a, o = synth.make_records(n, w["kind"], w["lo"], w["hi"], w["dup"], seed)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = oracle.canonicalize_batch(a, o, normalize=True, threads=cores, want_start=False, want_hash=False)
+        t1 = time.perf_counter()
+        if uniq:
+            oracle.uniq_consume(r["out"], o, r["lens"])
+        t2 = time.perf_counter()
+        if it >= warmup:
+            times.append(max(t1 - t0, t2 - t1))
+    sec = sum(times) / len(times)
+    bases = int(o[-1])
+    return dict(records_per_s=n / sec, gbases_per_s=bases / sec / 1e9, cores=cores, sample_records=n,
+                sample_bases=bases, ms_per_step=sec * 1e3)
+
+
+def cpu_faithful_footnote(w, seed):
+    """The reference AS WRITTEN indexes with s.chars().nth(i) (O(i) per access, lib/src/canonicalize.rs:18-25):
+    time that on a tiny sample and report records/s per core (extrapolated, labelled as such)."""
+    import oracle
+    from oracle import synth
+    n = 40 if w["hi"] <= 5000 else 2
+    a, o = synth.make_records(n, w["kind"], w["lo"], min(w["hi"], 20000), 0, seed)
+    t = time.perf_counter()
+    oracle.canonicalize_batch(a, o, normalize=True, threads=1, want_start=False, want_hash=False, faithful_cost=True)
+    dt = time.perf_counter() - t
+    return {"records_per_s_per_core": n / dt, "sample_records": n, "note": "extrapolated; O(n^2) chars().nth emulation"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = dict(WORKLOADS[args.workload])
+    seed = SEEDS[args.workload]
+    named = args.records == 0
+    if args.records:
+        w["records"] = args.records
+    metric = "canonicalize+uniq records/sec" if w["uniq"] else "canonicalize records/sec"
+    config = {"workload": w["desc"] + ("" if named else " [REDUCED: --records %d, not the named config]" % w["records"]),
+              "records_per_gpu": w["records"], "length_law": ["uniform", "log-uniform"][w["kind"]],
+              "length_range": [w["lo"], w["hi"]], "duplicate_fraction": w["dup"] / 1000.0,
+              "l2_policy": "inputs larger than L2 (packed arena + ASCII output per step >> 126 MB)",
+              "sharding": "contiguous input-index ranges per GPU; uniq keys exchanged by hash range (all-to-all)"}
+
+    # ---------------- reference arm: the CPU path, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_arm(w, seed, max(args.cpu_seconds, 4.0 * (args.steps + args.warmup)), args.steps, args.warmup, w["uniq"])
+        sample = ("oracle port of circKit's path (Duval x2 + revcomp + compare, xxh3, keep-first map; O(1) byte "
+                  "indexing -- conservative: the reference's chars().nth(i) is O(i)); %d records / %.1f Mbases of the "
+                  "workload per step, worker stage on %d threads, consumer stage serial, step = max of the two"
+                  % (r["sample_records"], r["sample_bases"] / 1e6, r["cores"]))
+        line = {"impl": "reference", "metric": metric, "value": r["records_per_s"], "unit": "records/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config, "gbases_per_s": r["gbases_per_s"],
+                "cpu_baseline": {"value": r["records_per_s"], "unit": "records/s", "cores": r["cores"], "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": r["records_per_s"], "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    import circkit_b200
+    from circkit_b200 import device as D
+    from circkit_b200 import exchange as X
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R = w["records"]
+    ctx = circkit_b200.Context(device=local_rank, max_batch_bytes=(256 << 20) if not args.no_e2e else 0,
+                               max_batch_records=(1 << 20) if not args.no_e2e else 0,
+                               table_capacity=R if (w["uniq"] and not args.no_e2e) else 0)
+    base_index = rank * R
+    batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
+                          dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
+    outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"])
+    ws = D.Workspace(ctx, R, 0, dev)
+    lens = batch.lens
+    if w["uniq"]:
+        table = D.DeviceTable(ctx, capacity_keys=int(R * 1.05) + 1024, dev=dev)   # owns ~R keys of the global set
+        first = torch.empty(R, dtype=torch.int64, device=dev)
+        slot_cache = {}
+
+        def first_fn(h, idx):
+            m = h.numel()
+            key = m
+            if key not in slot_cache:
+                slot_cache[key] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
+                                   torch.empty(max(m, 1), dtype=torch.int64, device=dev))
+            slots, out = slot_cache[key]
+            table.insert(h, m, slots, index=idx)
+            table.first(slots, m, out)
+            return out[:m]
+
+    def step():
+        D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
+        if w["uniq"]:
+            table.clear()
+            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn)
+            first.copy_(f)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    D.check(ctx, ws)
+    ctx._lib.ck_kernel_timing(ctx.handle, 1)
+    D.kernel_times(ctx)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    ktimes = D.kernel_times(ctx)
+    ctx._lib.ck_kernel_timing(ctx.handle, 0)
+    D.check(ctx, ws)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    total_records = R * world
+    total_bases = batch.total
+    if world > 1:
+        tb = torch.tensor([batch.total], dtype=torch.int64, device=dev)
+        dist.all_reduce(tb)
+        total_bases = int(tb.item())
+    value = total_records / (ms_per_step / 1e3)
+
+    # ---------------- roofline of the dominant kernel (rank 0's launches)
+    from circkit_b200.device import CLASS_NAMES
+    dom = max((c for c in CLASS_NAMES if ktimes[c][1]), key=lambda c: ktimes[c][0])
+    bounds = {"2bit_le_512": (1, 512), "2bit_le_8192": (513, 8192), "2bit_le_65536": (8193, 65536),
+              "2bit_le_425984": (65537, 425984)}
+    lo_n, hi_n = bounds.get(dom, (1, 1 << 40))
+    # bytes this kernel's launch moves by the algorithm: packed read + ASCII write + 16 (+8 hash write);
+    # the table's 32 B/record belong to the table kernels, not to this launch
+    sel = lens[(lens >= lo_n) & (lens <= hi_n)]
+    alg_bytes = int((8 * ((sel + 31) // 32) + sel + 16 + (8 if w["uniq"] else 0)).sum().item())
+    dom_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
+    roofline = {"bound": "hbm", "kernel": "k_canon_%s<%s> [%s]" % ("cta" if "65536" in dom or "425984" in dom else "warp",
+                                                                  dom.split("_")[0], dom),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_ms,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,
+                "step_ms": ms_per_step}
+
+    # ---------------- e2e through the host-buffer C ABI (pinned host memory, copies timed)
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        import numpy as np
+        ascii_dev = D.unpack_ascii(ctx, batch)
+        total = int(batch.total)
+        lib = ctx._lib
+        h_bytes_p = lib.ck_alloc_pinned(ctx.handle, total + 64)
+        h_bytes = np.ctypeslib.as_array(C.cast(h_bytes_p, C.POINTER(C.c_uint8)), shape=(total + 64,))
+        pinned_view = torch.from_numpy(h_bytes)
+        pinned_view[:total].copy_(ascii_dev)
+        del ascii_dev
+        off_host = batch.offsets.cpu().numpy().astype(np.uint64)
+        # batches of <= 256 MiB / <= 1 Mi records, alternating the two slots
+        max_b, max_r = 256 << 20, 1 << 20
+        cuts = [0]
+        while cuts[-1] < R:
+            lo_i = cuts[-1]
+            hi_i = min(R, lo_i + max_r)
+            limit = int(off_host[lo_i]) + max_b
+            if int(off_host[hi_i]) > limit:
+                hi_i = int(np.searchsorted(off_host, limit, side="right")) - 1
+            cuts.append(max(hi_i, lo_i + 1))
+        nb = len(cuts) - 1
+        rel_offs, pins = [], []
+        for b in range(nb):
+            ro = (off_host[cuts[b]: cuts[b + 1] + 1] - off_host[cuts[b]]).copy()
+            p = lib.ck_alloc_pinned(ctx.handle, ro.nbytes)
+            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(len(ro),))
+            arr[:] = ro
+            rel_offs.append(arr); pins.append(p)
+        out_first_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R + 1))
+        out_hash_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R + 1))
+        out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
+        out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
+        out_strand_p = lib.ck_alloc_pinned(ctx.handle, (R + 1))
+        flags = 2   # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record
+
+        def e2e_step():
+            if w["uniq"]:
+                ctx.uniq_reset()
+            for b in range(nb + 1):
+                if b < nb:
+                    bp = h_bytes_p + int(off_host[cuts[b]])
+                    nrec = cuts[b + 1] - cuts[b]
+                    if w["uniq"]:
+                        rc = lib.ck_uniq_submit(ctx.handle, b & 1, bp, rel_offs[b].ctypes.data, nrec, flags, base_index + cuts[b])
+                    else:
+                        rc = lib.ck_canon_submit(ctx.handle, b & 1, bp, rel_offs[b].ctypes.data, nrec, flags)
+                    ctx._check(rc)
+                if b >= 1:
+                    pb = b - 1
+                    c0 = cuts[pb]
+                    if w["uniq"]:
+                        rc = lib.ck_uniq_wait(ctx.handle, pb & 1, None, out_len_p + 4 * c0, out_hash_p + 8 * c0, out_first_p + 8 * c0)
+                    else:
+                        rc = lib.ck_canon_wait(ctx.handle, pb & 1, None, out_len_p + 4 * c0, out_start_p + 4 * c0,
+                                               out_strand_p + c0, None)
+                    ctx._check(rc)
+
+        e2e_step()                         # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = total + 8 * (R + nb)
+        d2h = (R * (8 + 8 + 4)) if w["uniq"] else (R * (4 + 4 + 1))
+        # parity spot check of the e2e result against the device-resident result (multi-rank: local keys only)
+        if w["uniq"] and world == 1:
+            got = np.ctypeslib.as_array(C.cast(out_first_p, C.POINTER(C.c_uint64)), shape=(R,))
+            assert np.array_equal(got, first.cpu().numpy().astype(np.uint64)), "e2e first_index != resident first_index"
+        e2e = {"value": total_records / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "batches_per_step": nb,
+               "api": "ck_uniq_submit/ck_uniq_wait" if w["uniq"] else "ck_canon_submit/ck_canon_wait",
+               "input": "ASCII record bytes + offsets in pinned host memory (normalise+pack on device)",
+               "result": "first_index + hash64 + length per record" if w["uniq"] else "start + strand + length per record",
+               "gbases_per_s": total_bases / (dt / e2e_steps) / 1e9,
+               "note": "multi-rank e2e dedups per rank (no exchange); the resident path does the global exchange" if world > 1 else ""}
+        for p in pins + [out_first_p, out_hash_p, out_len_p, out_start_p, out_strand_p, h_bytes_p]:
+            lib.ck_free_pinned(ctx.handle, p)
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_arm(w, seed, args.cpu_seconds, 3, 1, w["uniq"])
+        cpu = {"value": r["records_per_s"], "unit": "records/s", "cores": r["cores"], "kind": "port",
+               "gbases_per_s": r["gbases_per_s"],
+               "sample": "%d records / %.1f Mbases of the same length law and duplicate rate (independent numpy draw), "
+                         "worker stage on %d threads + serial consumer, step = max of the two; O(1)-indexed Duval "
+                         "(conservative)" % (r["sample_records"], r["sample_bases"] / 1e6, r["cores"]),
+               "faithful_cost_footnote": cpu_faithful_footnote(w, seed)}
+
+    if rank == 0:
+        survivors = int((first == torch.arange(base_index, base_index + R, device=dev)).sum().item()) if w["uniq"] else None
+        line = {"metric": metric, "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "gbases_per_s": total_bases / (ms_per_step / 1e3) / 1e9, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "rank0_unique_records": survivors}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

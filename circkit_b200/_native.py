@@ -50,6 +50,8 @@ SIGNATURES = {
     "ck_dev_table_insert": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _vp]),
     "ck_dev_table_first": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "ck_launch_count": (_u64, [_vp]),
+    "ck_kernel_timing": (_i, [_vp, _i]),
+    "ck_kernel_times": (_i, [_vp, _vp, _vp, _u32]),
     "ck_synth_offsets": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _u32, _u32, _u32, _vp, C.POINTER(_u64)]),
     "ck_synth_packed2": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp]),
     "ck_dev_unpack2": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),

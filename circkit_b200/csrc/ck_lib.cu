@@ -91,6 +91,9 @@ struct ck_ctx {
     TableSlot *table = nullptr; u64 table_slots = 0; u64 *side = nullptr; u32 *d_overflow = nullptr;
     u64 launches = 0;
     bool attrs_set = false;
+    // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 2];     // [CLS_COUNT] = table insert, [CLS_COUNT+1] = table first
 };
 
 namespace {
@@ -202,6 +205,11 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
         const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
         const u32 smem = kCls[c].bits ? cls_smem_bytes(c) : 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->timing) {
+            CK_CUDA(ctx, cudaEventCreate(&e0)); CK_CUDA(ctx, cudaEventCreate(&e1));
+            CK_CUDA(ctx, cudaEventRecord(e0, st));
+        }
         switch (c) {
         case CLS_W2S: case CLS_W2M: k_canon_warp<2><<<grid, thr, smem, st>>>(a); break;
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
@@ -210,6 +218,10 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         case CLS_W8: k_canon_warp<8><<<grid, thr, smem, st>>>(a); break;
         case CLS_C8: k_canon_cta<8, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, st>>>(a); break;
+        }
+        if (ctx->timing) {
+            CK_CUDA(ctx, cudaEventRecord(e1, st));
+            ctx->ev_pairs[c].push_back(e0); ctx->ev_pairs[c].push_back(e1);
         }
         ctx->launches++;
     }
@@ -610,6 +622,30 @@ int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_by
     return table_first(ctx, (cudaStream_t)stream, slots, nslots, side, U(slot_scratch), n, U(out_first_index));
 }
 uint64_t ck_launch_count(const ck_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ck_kernel_timing(ck_ctx *ctx, int enable)
+{
+    if (!ctx) return CK_ERR_ARG;
+    ctx->timing = enable != 0;
+    return CK_OK;
+}
+int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_t n_classes)
+{
+    if (!ctx || !out_ms || !out_launches) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
+    CK_CUDA(ctx, cudaDeviceSynchronize());
+    for (u32 c = 0; c < n_classes; c++) { out_ms[c] = 0; out_launches[c] = 0; }
+    for (u32 c = 0; c < (u32)CLS_COUNT + 2; c++) {
+        std::vector<cudaEvent_t> &v = ctx->ev_pairs[c];
+        for (size_t k = 0; k + 1 < v.size(); k += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, v[k], v[k + 1]);
+            if (c < n_classes) { out_ms[c] += ms; out_launches[c]++; }
+            cudaEventDestroy(v[k]); cudaEventDestroy(v[k + 1]);
+        }
+        v.clear();
+    }
+    return CK_OK;
+}
 
 // ---- synthetic workloads -------------------------------------------------------------------
 int ck_synth_offsets(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records, uint32_t kind,

@@ -1,0 +1,125 @@
+"""Device-resident front end: torch tensors as HBM buffers + current CUDA stream, kernels via the C ABI.
+
+torch is plumbing here (allocation, streams, torch.distributed); every kernel that touches record data
+is launched by libcirckit_b200.so.  64-bit unsigned buffers are carried as torch.int64 (same bits).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+from .core import Context
+
+CLASS_NAMES = ["2bit_le_512", "2bit_le_8192", "2bit_le_65536", "2bit_le_425984", "4bit_le_2048", "4bit_le_212992",
+               "byte_le_1024", "byte_le_106496", "huge", "empty"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class DeviceBatch:
+    """A packed 2-bit batch resident in HBM: offsets[int64, n+1], packed2[int64 words]."""
+
+    def __init__(self, offsets: torch.Tensor, packed2: torch.Tensor, n_records: int, total: int):
+        self.offsets, self.packed2, self.n, self.total = offsets, packed2, n_records, total
+
+    @property
+    def lens(self) -> torch.Tensor:
+        return self.offsets[1:] - self.offsets[:-1]
+
+
+def synth_batch(ctx: Context, *, seed: int, first_index: int, n_records: int, kind: int, lo: int, hi: int,
+                dup_permille: int = 0, adversarial_permille: int = 0, device=None) -> DeviceBatch:
+    """BASELINE.json synthetic records generated straight into the packed arena."""
+    dev = device or torch.device("cuda", ctx.device)
+    offsets = torch.empty(n_records + 1, dtype=torch.int64, device=dev)
+    total = C.c_uint64(0)
+    ctx._check(ctx._lib.ck_synth_offsets(ctx.handle, _stream(), seed, first_index, n_records, kind, lo, hi,
+                                         dup_permille, _p(offsets), C.byref(total)))
+    words = total.value // 32 + n_records + 2
+    packed2 = torch.empty(words, dtype=torch.int64, device=dev)
+    ctx._check(ctx._lib.ck_synth_packed2(ctx.handle, _stream(), seed, first_index, n_records, _p(offsets),
+                                         dup_permille, adversarial_permille, _p(packed2)))
+    return DeviceBatch(offsets, packed2, n_records, total.value)
+
+
+def unpack_ascii(ctx: Context, b: DeviceBatch, n_records: int | None = None) -> torch.Tensor:
+    """ASCII arena of the first n_records records (for the CPU baseline / parity checks)."""
+    n = b.n if n_records is None else n_records
+    total = int(b.offsets[n].item())
+    out = torch.empty(max(total, 1), dtype=torch.uint8, device=b.offsets.device)
+    ctx._check(ctx._lib.ck_dev_unpack2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), n, _p(out)))
+    return out[:total]
+
+
+class CanonOutputs:
+    def __init__(self, n: int, total: int, dev, want_bytes=True, want_hash=True):
+        self.out = torch.empty(max(total, 1) + 16, dtype=torch.uint8, device=dev) if want_bytes else None
+        self.start = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.strand = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        self.hash = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if want_hash else None
+
+
+class Workspace:
+    def __init__(self, ctx: Context, n_records: int, total_bytes: int = 0, dev=None):
+        self.bytes = int(ctx._lib.ck_dev_workspace_bytes(n_records, total_bytes))
+        self.buf = torch.empty(self.bytes, dtype=torch.uint8, device=dev or torch.device("cuda", ctx.device))
+
+
+def canon_packed2(ctx: Context, b: DeviceBatch, outs: CanonOutputs, ws: Workspace, class_mask: int = 0):
+    """k_classify + LMSR/canonical/XXH3 kernels over a resident batch (no copies, no sync)."""
+    ctx._check(ctx._lib.ck_dev_canon_packed2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), b.n, class_mask,
+                                             _p(outs.out), _p(outs.start), _p(outs.strand), _p(outs.hash),
+                                             _p(ws.buf), ws.bytes))
+
+
+def check(ctx: Context, ws: Workspace):
+    ctx._check(ctx._lib.ck_dev_check(ctx.handle, _stream(), _p(ws.buf)))
+
+
+class DeviceTable:
+    """First-occurrence table in HBM (src/uniq.rs:27,47-48 on device)."""
+
+    def __init__(self, ctx: Context, capacity_keys: int, dev=None):
+        self.ctx = ctx
+        self.bytes = int(ctx._lib.ck_dev_table_bytes(capacity_keys))
+        self.buf = torch.empty(self.bytes, dtype=torch.uint8, device=dev or torch.device("cuda", ctx.device))
+        self.clear()
+
+    def clear(self):
+        self.ctx._check(self.ctx._lib.ck_dev_table_clear(self.ctx.handle, _stream(), _p(self.buf), self.bytes))
+
+    def insert(self, hash64: torch.Tensor, n: int, slot_scratch: torch.Tensor, index: torch.Tensor | None = None,
+               base_index: int = 0):
+        self.ctx._check(self.ctx._lib.ck_dev_table_insert(self.ctx.handle, _stream(), _p(self.buf), self.bytes,
+                                                          _p(hash64), _p(index), base_index, n, _p(slot_scratch)))
+
+    def first(self, slot_scratch: torch.Tensor, n: int, out_first: torch.Tensor):
+        self.ctx._check(self.ctx._lib.ck_dev_table_first(self.ctx.handle, _stream(), _p(self.buf), self.bytes,
+                                                         _p(slot_scratch), n, _p(out_first)))
+
+
+def kernel_times(ctx: Context):
+    """{class name: (total ms, launches)} since the last call (needs ck_kernel_timing(1))."""
+    n = len(CLASS_NAMES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint32 * n)()
+    ctx._check(ctx._lib.ck_kernel_times(ctx.handle, ms, cnt, n))
+    return {CLASS_NAMES[i]: (ms[i], cnt[i]) for i in range(n)}
+
+
+def algorithmic_bytes(lens: torch.Tensor, uniq: bool, lo: int = 1, hi: int = 1 << 62) -> int:
+    """SURVEY §8d, 2-bit lane: 8*ceil(n/32) packed read + n ASCII write + 16 (offset read, start/strand write);
+    uniq adds 8 (hash write) + 32 (one 16-byte table slot read + write)."""
+    sel = lens[(lens >= lo) & (lens <= hi)]
+    b = (8 * ((sel + 31) // 32) + sel + 16).sum()
+    if uniq:
+        b = b + 40 * sel.numel()
+    return int(b.item())

@@ -1,0 +1,91 @@
+"""Hash-range exchange for multi-GPU uniq.
+
+Each rank canonicalises + hashes its contiguous shard; the owner of a key is the rank its top hash
+bits select; ranks exchange (hash64, global_index) with one personalised all-to-all, the owner keeps the
+minimum index per key (first occurrence in input order, src/uniq.rs:47-48), and a reverse all-to-all
+returns first_index to the record's home rank.  The result is independent of the rank count because
+min over global indices is associative and commutative.
+
+Written against torch.distributed only (NCCL on GPUs, gloo in the CPU tests); the per-owner
+first-occurrence step is passed in (`first_fn`) -- on GPUs it is the CUDA table of libcirckit_b200.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def owner_of(hash64: torch.Tensor, world: int) -> torch.Tensor:
+    """Owner rank = floor(hash * world / 2^64) computed on the top 32 bits (hash carried as int64 bits)."""
+    top = (hash64 >> 32) & 0xFFFFFFFF                      # arithmetic shift + mask == logical shift
+    return (top * world) >> 32
+
+
+def _all_to_all(send: torch.Tensor, send_counts: list[int], recv_counts: list[int], group=None) -> torch.Tensor:
+    recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_to_all_single(recv, send, recv_counts, send_counts, group=group)
+        return recv
+    # gloo has no all-to-all: personalised exchange with point-to-point ops
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    s_off = [0]
+    for c in send_counts:
+        s_off.append(s_off[-1] + c)
+    r_off = [0]
+    for c in recv_counts:
+        r_off.append(r_off[-1] + c)
+    recv[r_off[rank]: r_off[rank + 1]] = send[s_off[rank]: s_off[rank + 1]]
+    reqs = []
+    for p in range(world):
+        if p == rank:
+            continue
+        if send_counts[p]:
+            reqs.append(dist.isend(send[s_off[p]: s_off[p + 1]].contiguous(), p, group=group))
+    bufs = {}
+    for p in range(world):
+        if p == rank or not recv_counts[p]:
+            continue
+        bufs[p] = torch.empty(recv_counts[p], dtype=send.dtype, device=send.device)
+        reqs.append(dist.irecv(bufs[p], p, group=group))
+    for r in reqs:
+        r.wait()
+    for p, b in bufs.items():
+        recv[r_off[p]: r_off[p + 1]] = b
+    return recv
+
+
+def exchange_first_index(hash64: torch.Tensor, base_index: int,
+                         first_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], group=None) -> torch.Tensor:
+    """first_index[i] (global) for every local record i.
+
+    hash64     int64[n]  XXH3-64 of the local records' canonical forms (bit pattern)
+    base_index           global input index of local record 0 (shards are contiguous, rank order)
+    first_fn(h, idx) ->  int64[m]: for the items this rank owns, the minimum global index per key
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = hash64.numel()
+    gidx = torch.arange(base_index, base_index + n, dtype=torch.int64, device=hash64.device)
+    if world == 1:
+        return first_fn(hash64, gidx)
+    owner = owner_of(hash64, world)
+    order = torch.argsort(owner, stable=True)              # bucket by owner (order inside a bucket is free)
+    send_counts_t = torch.bincount(owner, minlength=world)
+    recv_counts_t = torch.empty_like(send_counts_t)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv_counts_t, send_counts_t, group=group)
+    else:
+        gathered = [torch.empty_like(send_counts_t) for _ in range(world)]
+        dist.all_gather(gathered, send_counts_t, group=group)
+        recv_counts_t = torch.stack(gathered)[:, dist.get_rank(group)].contiguous()
+    send_counts = [int(x) for x in send_counts_t.tolist()]
+    recv_counts = [int(x) for x in recv_counts_t.tolist()]
+    h_recv = _all_to_all(hash64[order].contiguous(), send_counts, recv_counts, group)
+    i_recv = _all_to_all(gidx[order].contiguous(), send_counts, recv_counts, group)
+    f_recv = first_fn(h_recv, i_recv)                      # owner side: min global index per key
+    f_back = _all_to_all(f_recv.contiguous(), recv_counts, send_counts, group)
+    first = torch.empty_like(f_back)
+    first[order] = f_back
+    return first

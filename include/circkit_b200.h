@@ -121,6 +121,11 @@ int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_by
                        uint32_t n, uint64_t *out_first_index);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ck_launch_count(const ck_ctx *ctx);
+/* per-class kernel timing for the roofline: when enabled, every length/alphabet-class launch is bracketed
+ * by CUDA events on its own stream; ck_kernel_times() synchronises, sums the elapsed ms and launch counts
+ * per class (index = class bit position of CK_CLASS_*) and clears the record. */
+int ck_kernel_timing(ck_ctx *ctx, int enable);
+int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_t n_classes);
 
 /* ---- synthetic workloads of BASELINE.json (device generators, bench + tests) ------------------
  * Record g = first_index + i is a pure function of (seed, g): any shard can be generated on any rank.
