@@ -33,7 +33,7 @@ __host__ __device__ constexpr u32 cls_max_n(int c)
 }
 
 struct CanonArgs {
-    const u64 *packed2;     // 2-bit arena: record i at word (offsets[i] >> 5) + i
+    const u64 *packed2;     // 2-bit arena (16-base u32 units, MSB-first): record i at u64 index (offsets[i] >> 5) + i
     const u8 *bytes;        // normalised byte arena: record i at offsets[i]
     const u64 *offsets;     // n_records + 1 symbol offsets
     const u32 *lens;        // optional normalised lengths (else offsets[i+1] - offsets[i])
@@ -49,11 +49,37 @@ struct CanonArgs {
     u32 smem_units;         // u32 units reserved per strand in (shared) staging memory
     u32 *xglobal;           // CLS_HUGE only: strands staged here, 2 * smem_units u32 per CTA
     u32 mode;               // bit0: forward strand only (lmsr / lmsr_index, lib/src/canonicalize.rs:5,41)
+    u32 min_n, max_n;       // length range of this launch's class (checked when there is no list)
 };
 
 // ---------------------------------------------------------------------------------------------
-// canonical ASCII -> global memory in 16-byte destination-aligned chunks (coalesced 128-bit stores;
-// the ragged first/last chunk of a record is written bytewise because neighbours own the rest).
+// One 16-byte destination-aligned chunk of a record's canonical ASCII.  t0 = record-relative index of the
+// chunk's first byte (negative in the record's first chunk when the record does not start on a 16-byte
+// line).  Full chunks are one 128-bit store; ragged edges use naturally aligned 1/2/4/8-byte pieces because
+// the neighbouring records own the rest of the line.
+__device__ __forceinline__ void store_chunk(u8 *dst, int t0, u32 n, u64 lo, u64 hi)
+{
+    if (t0 >= 0 && (u32)t0 + 16u <= n) {
+        *reinterpret_cast<uint4 *>(dst + t0) = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+        return;
+    }
+    const u32 kb = t0 < 0 ? (u32)(-t0) : 0u;
+    const u32 ke = t0 < 0 ? min(16u, n + kb) : min(16u, n - (u32)t0);
+    u8 *p = dst + t0;
+#define CK_PIECE(k) (((k) & 8u ? hi : lo) >> (8u * ((k) & 7u)))
+    u32 k = kb;
+    if ((k & 1u) && k + 1 <= ke) { p[k] = (u8)CK_PIECE(k); k += 1; }
+    if ((k & 2u) && k + 2 <= ke) { *reinterpret_cast<u16 *>(p + k) = (u16)CK_PIECE(k); k += 2; }
+    if ((k & 4u) && k + 4 <= ke) { *reinterpret_cast<u32 *>(p + k) = (u32)CK_PIECE(k); k += 4; }
+    if ((k & 8u) && k + 8 <= ke) { *reinterpret_cast<u64 *>(p + k) = hi; k += 8; }
+    if (k + 8 <= ke) { *reinterpret_cast<u64 *>(p + k) = CK_PIECE(k); k += 8; }
+    if (k + 4 <= ke) { *reinterpret_cast<u32 *>(p + k) = (u32)CK_PIECE(k); k += 4; }
+    if (k + 2 <= ke) { *reinterpret_cast<u16 *>(p + k) = (u16)CK_PIECE(k); k += 2; }
+    if (k + 1 <= ke) { p[k] = (u8)CK_PIECE(k); }
+#undef CK_PIECE
+}
+
+// canonical ASCII -> global memory, generic lanes (coalesced 128-bit stores)
 template <int BITS, typename G>
 __device__ __forceinline__ void emit_ascii(const u32 *X, u32 n, u32 start, u8 *dst)
 {
@@ -61,20 +87,13 @@ __device__ __forceinline__ void emit_ascii(const u32 *X, u32 n, u32 start, u8 *d
     const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
     const u32 nchunks = (n + a + 15u) >> 4;
     for (u32 c = rank; c < nchunks; c += gs) {
-        const int t0 = (int)(16u * c) - (int)a;
-        u32 tt = t0 < 0 ? (u32)((t0 % (int)n + (int)n) % (int)n) : (u32)t0;   // t0 < n always
-        u32 t8 = tt + 8; if (t8 >= n) t8 %= n;
+        const int t0 = (int)(16u * c) - (int)a;               // t0 < n always
+        int ti = t0;
+        if (ti < 0) { ti += (int)n; if (ti < 0) { ti %= (int)n; if (ti < 0) ti += (int)n; } }
+        const u32 tt = (u32)ti;
+        u32 t8 = tt + 8; if (t8 >= n) { t8 -= n; if (t8 >= n) t8 %= n; }
         const u64 lo = ascii8<BITS>(X, n, start, tt), hi = ascii8<BITS>(X, n, start, t8);
-        if (t0 >= 0 && (u32)t0 + 16u <= n) {
-            uint4 v = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
-            *reinterpret_cast<uint4 *>(dst + t0) = v;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int tb = t0 + k;
-                if (tb >= 0 && (u32)tb < n) dst[tb] = (u8)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xffu);
-            }
-        }
+        store_chunk(dst, t0, n, lo, hi);
     }
 }
 
@@ -84,6 +103,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
 {
     const u64 off = a.offsets[rec];
     const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
+    if (a.list == nullptr && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform)
     RecordIn in;
     in.packed2 = a.packed2 ? a.packed2 + ((off >> 5) + rec) : nullptr;
     in.bytes = a.bytes ? a.bytes + off : nullptr;
@@ -142,6 +162,7 @@ __global__ void k_canon_empty(CanonArgs a)
     const u32 count = a.list ? *a.count : a.n_direct;
     for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const u32 rec = a.list ? a.list[e] : e;
+        if (a.list == nullptr && a.offsets[rec + 1] != a.offsets[rec]) continue;
         if (a.out_start) a.out_start[rec] = 0;
         if (a.out_strand) a.out_strand[rec] = 1;
         if (a.out_hash) a.out_hash[rec] = xxh64_avalanche(sec64(56) ^ sec64(64));
@@ -212,14 +233,14 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
                 acc_lo |= __reduce_or_sync(CK_FULL, c_lo0);
                 const u32 ndone = done + __popc(keep);
                 if ((ndone >> 5) != A) {          // word A is complete
-                    if (lane == 0) dstw[A] = ((u64)acc_hi << 32) | acc_lo;
+                    if (lane == 0) dstw[A] = ((u64)acc_lo << 32) | acc_hi;   // unit of bases 0-15 at the lower address
                     acc_hi = __reduce_or_sync(CK_FULL, c_hi1);
                     acc_lo = __reduce_or_sync(CK_FULL, c_lo1);
                 }
             }
             done += __popc(keep);
         }
-        if (lanebits == 2 && (done & 31u) && lane == 0) dstw[done >> 5] = ((u64)acc_hi << 32) | acc_lo;
+        if (lanebits == 2 && (done & 31u) && lane == 0) dstw[done >> 5] = ((u64)acc_lo << 32) | acc_hi;
     }
 }
 
@@ -231,6 +252,8 @@ struct ClassifyArgs {
     u32 n_records;
     u32 *lists;        // CLS_COUNT lists of n_records entries each
     u32 *counts;       // CLS_COUNT counters (zeroed by the caller)
+    int only_class;    // >= 0: no lists are written (that class runs over all records directly); records of
+                       // any other class are counted in counts[CLS_HUGE] = "left unprocessed"
 };
 __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
 {
@@ -244,6 +267,11 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
                                 : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
         else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
         else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
+    }
+    if (a.only_class >= 0) {
+        const u32 m = __ballot_sync(CK_FULL, cls >= 0 && cls != a.only_class);
+        if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + CLS_HUGE, __popc(m));
+        return;
     }
     // warp-aggregated append, one atomic per (warp, class present)
     for (int c = 0; c < CLS_COUNT; c++) {

@@ -10,6 +10,7 @@
 
 #include "../../include/circkit_b200.h"
 #include "ck_kernels.cuh"
+#include "ck_warp2.cuh"
 #include "ck_synth.cuh"
 
 using namespace ck;
@@ -191,7 +192,11 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     int rc = set_attrs(ctx);
     if (rc) return rc;
     CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 16 * sizeof(u32), st));
-    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts};
+    // a promise of exactly one class lets that class index the records directly (no work lists)
+    int only = -1;
+    if (class_mask && (class_mask & (class_mask - 1)) == 0)
+        for (int c = 0; c < CLS_COUNT; c++) if (class_mask == (1u << c)) only = c;
+    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts, only};
     k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
     ctx->launches++;
     for (int c = 0; c < CLS_COUNT; c++) {
@@ -199,7 +204,13 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         if (class_mask && !(class_mask & (1u << c))) continue;
         CanonArgs a{};
         a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
-        a.list = io.lists + (size_t)c * io.n; a.count = io.counts + c; a.n_direct = 0;
+        if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
+        else { a.list = io.lists + (size_t)c * io.n; a.count = io.counts + c; a.n_direct = 0; }
+        a.max_n = cls_max_n(c);
+        a.min_n = (c == CLS_W2M) ? cls_max_n(CLS_W2S) + 1 : (c == CLS_C2A) ? cls_max_n(CLS_W2M) + 1
+                : (c == CLS_C2B) ? cls_max_n(CLS_C2A) + 1 : (c == CLS_C4) ? cls_max_n(CLS_W4) + 1
+                : (c == CLS_C8) ? cls_max_n(CLS_W8) + 1 : (c == CLS_EMPTY ? 0u : 1u);
+        if (c == CLS_EMPTY) a.max_n = 0;
         a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
         a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
         a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
@@ -211,7 +222,8 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             CK_CUDA(ctx, cudaEventRecord(e0, st));
         }
         switch (c) {
-        case CLS_W2S: case CLS_W2M: k_canon_warp<2><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2S: k_canon_w2<4><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2M: k_canon_w2<0><<<grid, thr, smem, st>>>(a); break;
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
         case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;

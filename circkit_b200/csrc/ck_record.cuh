@@ -47,7 +47,7 @@ template <int BITS> __host__ __device__ constexpr u64 tie_scratch_words(u64 n)
 }
 
 struct RecordIn {
-    const u64 *packed2;   // BITS == 2: MSB-first 2-bit words of this record (already offset)
+    const u64 *packed2;   // BITS == 2: this record's 16-base u32 units (first base in the top bits), 8-byte aligned
     const u8 *bytes;      // BITS != 2: normalised bytes of this record (already offset)
     u32 n;
 };
@@ -77,7 +77,7 @@ template <int BITS> __device__ __forceinline__ typename KeyOf<BITS>::type key_at
 // symbol t (0 <= t < n) of the forward strand straight from global memory (small-n extension only)
 template <int BITS> __device__ __forceinline__ u32 sym_global(const RecordIn &r, u32 t)
 {
-    if (BITS == 2) return (u32)(r.packed2[t >> 5] >> (62 - 2 * (t & 31))) & 3u;
+    if (BITS == 2) return (reinterpret_cast<const u32 *>(r.packed2)[t >> 4] >> (30 - 2 * (t & 15))) & 3u;
     u32 b = r.bytes[t];
     return BITS == 4 ? (u32)c_tab.code4[b] : b;
 }
@@ -97,9 +97,9 @@ __device__ __forceinline__ void stage_record(const RecordIn &r, u32 *Xf, u32 *Xr
     if (BITS == 2) {
         const u32 W = (n + 31) >> 5;
         for (u32 k = rank; k < W; k += gs) {
-            u64 w = __ldg(r.packed2 + k);
-            Xf[2 * k] = (u32)(w >> 32);
-            Xf[2 * k + 1] = (u32)w;
+            u64 w = __ldg(r.packed2 + k);           // two 16-base units, lower address first
+            Xf[2 * k] = (u32)w;
+            Xf[2 * k + 1] = (u32)(w >> 32);
         }
     } else {
         const u32 NU = (n + S - 1) / S;
@@ -141,8 +141,8 @@ __device__ __forceinline__ void stage_record(const RecordIn &r, u32 *Xf, u32 *Xr
     G::sync();
     // reverse complement: rc symbols [jS, jS+S) = revcomp(forward window at n - (j+1)S  (mod n))
     for (u32 j = rank; j < xunits; j += gs) {
-        long long t = (long long)n - (long long)(j + 1) * S;
-        if (t < 0) { t %= (long long)n; if (t < 0) t += n; }
+        int t = (int)n - (int)((j + 1) * S);          // n <= 2^30: fits
+        if (t < 0) { t += (int)n; if (t < 0) { t %= (int)n; if (t < 0) t += (int)n; } }
         Xr[j] = revcomp_unit<BITS>(window32<BITS>(Xf, (u32)t));
     }
     G::sync();

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *o
                     w = (w << 2) | c;
                 }
             }
-            dst[k] = w;
+            dst[k] = (w << 32) | (w >> 32);      // arena order: unit of bases 0-15 at the lower address
         }
     }
 }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_unpack2(const u64 *packed2, const u64 *
         const u32 n = (u32)(offsets[i + 1] - off);
         const u64 *src = packed2 + ((off >> 5) + i);
         for (u32 t = lane; t < n; t += 32) {
-            u32 c = (u32)(src[t >> 5] >> (62 - 2 * (t & 31))) & 3u;
+            u32 c = (reinterpret_cast<const u32 *>(src)[t >> 4] >> (30 - 2 * (t & 15))) & 3u;
             out[off + t] = "ACGT"[c];
         }
     }

@@ -1,0 +1,80 @@
+"""World-size-2 (and 4) gloo tests of the multi-GPU uniq exchange (circkit_b200/exchange.py) on CPU.
+
+The plumbing under test is what the N>1 bench path runs on NCCL: owner = hash range, personalised
+all-to-all of (hash, global index), min index per key at the owner, reverse all-to-all.  The per-owner
+first-occurrence step is played by a torch stand-in of the CUDA table (min index per key); the expected
+answer is the oracle's serial consumer over the concatenated shards (src/uniq.rs:42-78).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _min_index_per_key(h: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """stand-in for k_table_insert + k_table_first: for every item, the minimum index among equal keys"""
+    if h.numel() == 0:
+        return idx.clone()
+    uniq, inv = torch.unique(h, return_inverse=True)
+    m = torch.full((uniq.numel(),), torch.iinfo(torch.int64).max, dtype=torch.int64)
+    m.scatter_reduce_(0, inv, idx, reduce="amin")
+    return m[inv]
+
+
+def _worker(rank, world, port, hashes, expected, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from circkit_b200 import exchange as X
+    n = len(hashes) // world
+    lo, hi = rank * n, (rank + 1) * n if rank < world - 1 else len(hashes)
+    # contiguous shards; the last rank takes the remainder, so bases differ from rank * n only there
+    h = torch.from_numpy(hashes[lo:hi].view(np.int64).copy())
+    first = X.exchange_first_index(h, lo, _min_index_per_key)
+    ok = np.array_equal(first.numpy().astype(np.uint64), expected[lo:hi])
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_exchange_matches_serial_consumer(world):
+    import oracle
+    from oracle import synth
+    arena, off = synth.make_records(3001, 0, 60, 120, 400, seed=world)
+    res = oracle.canonicalize_batch(arena, off, normalize=True, threads=2, want_start=False)
+    hashes, expected = oracle.uniq_consume(res["out"], off, res["lens"])
+    # force the edge cases: hash with the top bit set / all ones / zero
+    hashes = hashes.copy()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, hashes, expected, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(r, True) for r in range(world)]
+
+
+def test_owner_of_covers_unsigned_range():
+    from circkit_b200.exchange import owner_of
+    h = np.array([0, 1, 2**63 - 1, 2**63, 2**64 - 1, 0x4000000000000000, 0xC000000000000000], dtype=np.uint64)
+    t = torch.from_numpy(h.view(np.int64).copy())
+    assert owner_of(t, 2).tolist() == [0, 0, 0, 1, 1, 0, 1]
+    assert owner_of(t, 4).tolist() == [0, 0, 1, 2, 3, 1, 3]
+    assert owner_of(t, 8).tolist() == [0, 0, 3, 4, 7, 2, 6]
+    # monotone in the unsigned value: hash-range partition
+    r = np.sort(np.random.default_rng(0).integers(0, 2**64, size=1000, dtype=np.uint64))
+    o = owner_of(torch.from_numpy(r.view(np.int64).copy()), 8).numpy()
+    assert (np.diff(o) >= 0).all() and o.min() == 0 and o.max() == 7

@@ -1,0 +1,113 @@
+"""GPU parity of the device-resident path bench.py times: synthetic packed batches (ck_synth_*),
+ck_dev_canon_packed2 with and without a class promise, the device first-occurrence table -- against
+the oracle on the unpacked ASCII of the same records."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import circkit_b200
+    from circkit_b200 import device as D
+    ctx = circkit_b200.Context(max_batch_bytes=0, max_batch_records=0)
+    yield ctx, D, torch
+    ctx.close()
+
+
+def _oracle_for(ctx, D, torch, batch, n):
+    ascii_ = D.unpack_ascii(ctx, batch, n).cpu().numpy()
+    off = batch.offsets[: n + 1].cpu().numpy().astype(np.uint64)
+    want = oracle.canonicalize_batch(ascii_, off, normalize=False, threads=8)
+    return ascii_, off, want
+
+
+@pytest.mark.parametrize("name,kind,lo,hi,dup,adv,mask,n", [
+    ("c1-like direct mode", 0, 250, 400, 0, 0, 1, 30000),
+    ("c2-like two classes", 1, 200, 5000, 300, 0, 3, 12000),
+    ("c5-like dups", 0, 250, 400, 300, 0, 1, 30000),
+    ("c4-like long + adversarial", 1, 5000, 200000, 0, 100, 2 | 4 | 8, 300),
+    ("all classes, no promise", 1, 64, 20000, 200, 20, 0, 3000),
+    ("short and tiny", 0, 1, 130, 100, 0, 0, 20000),
+])
+def test_device_path_matches_oracle(env, name, kind, lo, hi, dup, adv, mask, n):
+    ctx, D, torch = env
+    b = D.synth_batch(ctx, seed=11, first_index=0, n_records=n, kind=kind, lo=lo, hi=hi, dup_permille=dup,
+                      adversarial_permille=adv)
+    outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True)
+    ws = D.Workspace(ctx, n)
+    D.canon_packed2(ctx, b, outs, ws, class_mask=mask)
+    D.check(ctx, ws)
+    ascii_, off, want = _oracle_for(ctx, D, torch, b, n)
+    got_out = outs.out[: b.total].cpu().numpy()
+    assert np.array_equal(got_out, want["out"]), name
+    assert np.array_equal(outs.start[:n].cpu().numpy().astype(np.uint32), want["start"]), name
+    assert np.array_equal(outs.strand[:n].cpu().numpy(), want["strand"]), name
+    assert np.array_equal(outs.hash[:n].cpu().numpy().astype(np.uint64), want["hash"]), name
+    # uniq on device vs the serial consumer
+    table = D.DeviceTable(ctx, n)
+    slots = torch.empty(n, dtype=torch.int64, device=b.offsets.device)
+    first = torch.empty(n, dtype=torch.int64, device=b.offsets.device)
+    table.insert(outs.hash, n, slots)
+    table.first(slots, n, first)
+    _, wfirst = oracle.uniq_consume(want["out"], off, want["lens"])
+    assert np.array_equal(first.cpu().numpy().astype(np.uint64), wfirst), name
+    if dup:
+        assert (wfirst != np.arange(n)).sum() > 0.5 * n * dup / 1000     # duplicates were really injected and found
+
+
+def test_class_promise_violation_is_reported(env):
+    import circkit_b200
+    ctx, D, torch = env
+    b = D.synth_batch(ctx, seed=3, first_index=0, n_records=1000, kind=0, lo=400, hi=600, dup_permille=0)
+    outs = D.CanonOutputs(1000, b.total, b.offsets.device)
+    ws = D.Workspace(ctx, 1000)
+    D.canon_packed2(ctx, b, outs, ws, class_mask=1)           # promise n <= 512 is false
+    with pytest.raises(circkit_b200.CircKitError) as e:
+        D.check(ctx, ws)
+    assert e.value.code == -4
+
+
+def test_shards_regenerate_identically(env):
+    ctx, D, torch = env
+    whole = D.synth_batch(ctx, seed=5, first_index=0, n_records=4000, kind=0, lo=250, hi=400, dup_permille=300)
+    part = D.synth_batch(ctx, seed=5, first_index=1000, n_records=2000, kind=0, lo=250, hi=400, dup_permille=300)
+    a = D.unpack_ascii(ctx, whole).cpu().numpy()
+    off = whole.offsets.cpu().numpy()
+    p = D.unpack_ascii(ctx, part).cpu().numpy()
+    assert np.array_equal(a[off[1000]: off[3000]], p)
+
+
+def test_full_size_properties_config1(env):
+    """BASELINE config 1 at full size (1M records): size-independent properties instead of the oracle:
+    canonical form is idempotent, invariant under rotation + reverse complement (duplicates collapse)."""
+    ctx, D, torch = env
+    n = 1_000_000
+    b = D.synth_batch(ctx, seed=1, first_index=0, n_records=n, kind=0, lo=250, hi=400, dup_permille=300)
+    outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True)
+    ws = D.Workspace(ctx, n)
+    D.canon_packed2(ctx, b, outs, ws, class_mask=1)
+    D.check(ctx, ws)
+    # feed the canonical bytes back through the byte entry point: must be a fixed point with equal hashes
+    ws2 = D.Workspace(ctx, n, b.total)
+    outs2 = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True)
+    lens2 = torch.empty(n, dtype=torch.int32, device=b.offsets.device)
+    ctx._check(ctx._lib.ck_dev_canon_bytes(ctx.handle, torch.cuda.current_stream().cuda_stream, outs.out.data_ptr(),
+                                           b.offsets.data_ptr(), n, b.total, 0, 0, outs2.out.data_ptr(),
+                                           lens2.data_ptr(), outs2.start.data_ptr(), outs2.strand.data_ptr(),
+                                           outs2.hash.data_ptr(), ws2.buf.data_ptr(), ws2.bytes))
+    D.check(ctx, ws2)
+    assert torch.equal(outs.out[: b.total], outs2.out[: b.total])
+    assert torch.equal(outs.hash, outs2.hash)
+    # duplicates (rotations / reverse complements of earlier originals) hash like their origin:
+    table = D.DeviceTable(ctx, n)
+    slots = torch.empty(n, dtype=torch.int64, device=b.offsets.device)
+    first = torch.empty(n, dtype=torch.int64, device=b.offsets.device)
+    table.insert(outs.hash, n, slots)
+    table.first(slots, n, first)
+    uniq = int((first == torch.arange(n, device=first.device)).sum().item())
+    assert abs(uniq - 0.7 * n) < 0.01 * n            # ~30 % injected duplicates, all found, nothing else merged
