@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libcirckit_b200.so")
 
 CK_OK = 0
 CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5
-CK_F_NORMALIZE, CK_F_NO_BYTES = 1, 2
+CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT = 1, 2, 4
 CK_CLASS_2BIT_LE_512, CK_CLASS_2BIT_LE_8192, CK_CLASS_2BIT_LE_65536, CK_CLASS_2BIT_LE_425984 = 1, 2, 4, 8
 
 
@@ -42,7 +42,8 @@ SIGNATURES = {
     "ck_canonicalize": (_i, [_vp, _vp, _sz, _vp]),
     "ck_lmsr_index_batch": (_i, [_vp, _vp, _vp, _u32, _vp]),
     "ck_dev_workspace_bytes": (_u64, [_u32, _u64]),
-    "ck_dev_canon_packed2": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64]),
+    "ck_out_arena_bytes": (_u64, [_u64, _u32]),
+    "ck_dev_canon_packed2": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64]),
     "ck_dev_canon_bytes": (_i, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u64]),
     "ck_dev_check": (_i, [_vp, _vp, _vp]),
     "ck_dev_table_bytes": (_u64, [_u64]),

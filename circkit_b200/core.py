@@ -87,47 +87,66 @@ class Context:
         return out[:n]
 
     # -- batch API (host buffers)
-    def canon_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool, no_bytes=False):
-        flags = (N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+    def out_arena_bytes(self, total: int, n: int) -> int:
+        """Size of the CK_F_ALIGNED_OUT output arena (record i at 16 * ((offsets[i] >> 4) + i))."""
+        return int(self._lib.ck_out_arena_bytes(total, n))
+
+    @staticmethod
+    def aligned_starts(offsets: np.ndarray) -> np.ndarray:
+        """Byte position of every record in the aligned output arena."""
+        off = np.asarray(offsets[:-1], dtype=np.uint64)
+        return 16 * ((off >> np.uint64(4)) + np.arange(len(off), dtype=np.uint64))
+
+    def canon_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool, no_bytes=False,
+                     aligned=False):
+        flags = ((N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+                 | (N.CK_F_ALIGNED_OUT if aligned else 0))
         self._check(self._lib.ck_canon_submit(self._h, slot, _ptr(arena), _ptr(offsets), len(offsets) - 1, flags))
 
-    def canon_wait(self, slot: int, n: int, total: int, *, want_bytes=True):
-        out = np.zeros(max(total, 1), dtype=np.uint8) if want_bytes else None
+    def canon_wait(self, slot: int, n: int, total: int, *, want_bytes=True, aligned=False):
+        nbytes = self.out_arena_bytes(total, n) if aligned else total
+        out = np.zeros(max(nbytes, 1), dtype=np.uint8) if want_bytes else None
         lens = np.zeros(max(n, 1), dtype=np.uint32)
         start = np.zeros(max(n, 1), dtype=np.uint32)
         strand = np.zeros(max(n, 1), dtype=np.uint8)
         h = np.zeros(max(n, 1), dtype=np.uint64)
         self._check(self._lib.ck_canon_wait(self._h, slot, _ptr(out), _ptr(lens), _ptr(start), _ptr(strand), _ptr(h)))
-        return dict(out=None if out is None else out[:total], lens=lens[:n], start=start[:n], strand=strand[:n], hash=h[:n])
+        return dict(out=None if out is None else out[:nbytes], lens=lens[:n], start=start[:n], strand=strand[:n], hash=h[:n])
 
-    def canonicalize_batch(self, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, want_bytes=True):
-        """Worker closure over a batch (src/canonicalize.rs:21-30): returns dict(out, lens, start, strand, hash)."""
+    def canonicalize_batch(self, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, want_bytes=True,
+                           aligned=False):
+        """Worker closure over a batch (src/canonicalize.rs:21-30): returns dict(out, lens, start, strand, hash).
+        aligned=True: `out` is the 16-byte-aligned arena (record i at aligned_starts(offsets)[i])."""
         arena = np.ascontiguousarray(arena, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        self.canon_submit(0, arena, offsets, normalize=normalize, no_bytes=not want_bytes)
-        return self.canon_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes)
+        self.canon_submit(0, arena, offsets, normalize=normalize, no_bytes=not want_bytes, aligned=aligned)
+        return self.canon_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes,
+                               aligned=aligned)
 
     def uniq_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, base_index: int, *, normalize: bool,
-                    no_bytes=False):
-        flags = (N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+                    no_bytes=False, aligned=False):
+        flags = ((N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
+                 | (N.CK_F_ALIGNED_OUT if aligned else 0))
         self._check(self._lib.ck_uniq_submit(self._h, slot, _ptr(arena), _ptr(offsets), len(offsets) - 1, flags,
                                              base_index))
 
-    def uniq_wait(self, slot: int, n: int, total: int, *, want_bytes=True):
-        out = np.zeros(max(total, 1), dtype=np.uint8) if want_bytes else None
+    def uniq_wait(self, slot: int, n: int, total: int, *, want_bytes=True, aligned=False):
+        nbytes = self.out_arena_bytes(total, n) if aligned else total
+        out = np.zeros(max(nbytes, 1), dtype=np.uint8) if want_bytes else None
         lens = np.zeros(max(n, 1), dtype=np.uint32)
         h = np.zeros(max(n, 1), dtype=np.uint64)
         first = np.zeros(max(n, 1), dtype=np.uint64)
         self._check(self._lib.ck_uniq_wait(self._h, slot, _ptr(out), _ptr(lens), _ptr(h), _ptr(first)))
-        return dict(out=None if out is None else out[:total], lens=lens[:n], hash=h[:n], first=first[:n])
+        return dict(out=None if out is None else out[:nbytes], lens=lens[:n], hash=h[:n], first=first[:n])
 
     def uniq_batch(self, arena: np.ndarray, offsets: np.ndarray, base_index: int = 0, *, normalize: bool = False,
-                   want_bytes=True):
+                   want_bytes=True, aligned=False):
         """Worker + consumer closures over a batch (src/uniq.rs:33-78): dict(out, lens, hash, first)."""
         arena = np.ascontiguousarray(arena, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        self.uniq_submit(0, arena, offsets, base_index, normalize=normalize, no_bytes=not want_bytes)
-        return self.uniq_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes)
+        self.uniq_submit(0, arena, offsets, base_index, normalize=normalize, no_bytes=not want_bytes, aligned=aligned)
+        return self.uniq_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes,
+                              aligned=aligned)
 
     def uniq_reset(self):
         self._check(self._lib.ck_uniq_reset(self._h))

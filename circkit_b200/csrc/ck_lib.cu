@@ -57,6 +57,7 @@ u64 cls_tie_words(int c)
 u32 cls_smem_bytes(int c)
 {
     const u32 per = 2u * cls_units(c) * 4u;
+    if (c == CLS_W2S || c == CLS_W2M) return (u32)sizeof(W2Const) + per * (kCls[c].threads / 32u);
     return kCls[c].cta ? per : per * (kCls[c].threads / 32u);
 }
 
@@ -172,6 +173,7 @@ int set_attrs(ck_ctx *ctx)
     if (ctx->attrs_set) return CK_OK;
     int rc;
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
+    if ((rc = set_smem(ctx, k_canon_w2<false>, cls_smem_bytes(CLS_W2M)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
     ctx->attrs_set = true;
@@ -222,8 +224,8 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             CK_CUDA(ctx, cudaEventRecord(e0, st));
         }
         switch (c) {
-        case CLS_W2S: k_canon_w2<4><<<grid, thr, smem, st>>>(a); break;
-        case CLS_W2M: k_canon_w2<0><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2S: k_canon_w2<true><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2M: k_canon_w2<false><<<grid, thr, smem, st>>>(a); break;
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
         case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;
@@ -293,7 +295,7 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     ctx->launches++;
     CanonIO io{};
     io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = s.d_len; io.lane = s.d_lane;
-    io.n = n_records; io.mode = 0;
+    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.counts = s.d_counts;
@@ -328,7 +330,8 @@ int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *
     cudaStream_t st = s.stream;
     const size_t n = s.n;
     if (out_bytes && !(s.flags & CK_F_NO_BYTES) && s.total)
-        CK_CUDA(ctx, cudaMemcpyAsync(out_bytes, s.d_out, s.total, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(ctx, cudaMemcpyAsync(out_bytes, s.d_out, (s.flags & CK_F_ALIGNED_OUT) ? ck_out_arena_bytes(s.total, s.n) : s.total,
+                                     cudaMemcpyDeviceToHost, st));
     if (out_len) CK_CUDA(ctx, cudaMemcpyAsync(out_len, s.d_len, n * 4, cudaMemcpyDeviceToHost, st));
     if (out_start) CK_CUDA(ctx, cudaMemcpyAsync(out_start, s.d_start, n * 4, cudaMemcpyDeviceToHost, st));
     if (out_strand) CK_CUDA(ctx, cudaMemcpyAsync(out_strand, s.d_strand, n, cudaMemcpyDeviceToHost, st));
@@ -375,7 +378,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaEventCreateWithFlags(&s.inserted, cudaEventDisableTiming));
             CK_INIT(cudaMalloc(&s.d_raw, B + 16));
             CK_INIT(cudaMalloc(&s.d_norm, B + 16));
-            CK_INIT(cudaMalloc(&s.d_out, B + 16));
+            CK_INIT(cudaMalloc(&s.d_out, B + 16 * R + 64));
             CK_INIT(cudaMalloc(&s.d_p2, (B / 32 + R + 2) * 8));
             CK_INIT(cudaMalloc(&s.d_off, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_len, (R + 1) * 4));
@@ -552,15 +555,18 @@ uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
     if (total_bytes) b += (total_bytes / 32 + n_records + 2) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
     return (b + 255) & ~255ull;
 }
+uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records) { return 16ull * ((total_bytes >> 4) + n_records) + 16; }
+
 int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records,
-                         uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand,
+                         uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand,
                          uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes)
 {
     if (!ctx) return CK_ERR_ARG;
     if (workspace_bytes < ck_dev_workspace_bytes(n_records, 0)) return fail(ctx, CK_ERR_ARG, "workspace too small");
     CanonIO io{};
     io.packed2 = U(packed2); io.offsets = U(offsets); io.n = n_records;
-    io.out = out_bytes; io.out_start = out_start; io.out_strand = out_strand; io.out_hash = U(out_hash64);
+    io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
+    io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand; io.out_hash = U(out_hash64);
     io.counts = (u32 *)workspace; io.lists = (u32 *)((u8 *)workspace + 256);
     return run_canon(ctx, (cudaStream_t)stream, ctx->dev_scr, io, class_mask);
 }
@@ -586,6 +592,7 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     ctx->launches++;
     CanonIO io{};
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
+    io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand;
     io.out_hash = U(out_hash64); io.counts = counts; io.lists = lists;
     return run_canon(ctx, st, ctx->dev_scr, io, class_mask);

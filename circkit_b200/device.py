@@ -60,8 +60,10 @@ def unpack_ascii(ctx: Context, b: DeviceBatch, n_records: int | None = None) -> 
 
 
 class CanonOutputs:
-    def __init__(self, n: int, total: int, dev, want_bytes=True, want_hash=True):
-        self.out = torch.empty(max(total, 1) + 16, dtype=torch.uint8, device=dev) if want_bytes else None
+    def __init__(self, n: int, total: int, dev, want_bytes=True, want_hash=True, aligned=False):
+        self.aligned = aligned
+        nbytes = 16 * ((total >> 4) + n) + 16 if aligned else max(total, 1) + 16
+        self.out = torch.empty(nbytes, dtype=torch.uint8, device=dev) if want_bytes else None
         self.start = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.strand = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
         self.hash = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if want_hash else None
@@ -75,7 +77,8 @@ class Workspace:
 
 def canon_packed2(ctx: Context, b: DeviceBatch, outs: CanonOutputs, ws: Workspace, class_mask: int = 0):
     """k_classify + LMSR/canonical/XXH3 kernels over a resident batch (no copies, no sync)."""
-    ctx._check(ctx._lib.ck_dev_canon_packed2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), b.n, class_mask,
+    flags = (N.CK_F_ALIGNED_OUT if outs.aligned else 0) | (0 if outs.out is not None else N.CK_F_NO_BYTES)
+    ctx._check(ctx._lib.ck_dev_canon_packed2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), b.n, flags, class_mask,
                                              _p(outs.out), _p(outs.start), _p(outs.strand), _p(outs.hash),
                                              _p(ws.buf), ws.bytes))
 

@@ -45,6 +45,11 @@ extern "C" {
                                src/canonicalize.rs:24-27); without it bytes are used as they are, like
                                circkit::canonicalize (lib/src/canonicalize.rs:54) */
 #define CK_F_NO_BYTES 2u    /* do not produce canonical bytes (start/strand/hash only) */
+#define CK_F_ALIGNED_OUT 4u /* canonical bytes go to a 16-byte-aligned arena: record i starts at byte
+                               16 * ((offsets[i] >> 4) + i) of out_bytes (ck_out_arena_bytes() long) instead of
+                               offsets[i].  Every device store is then a full 128-bit store; the host writer reads
+                               each record from its aligned start (it copies record by record anyway:
+                               src/canonicalize.rs:33-37). */
 
 typedef struct ck_ctx ck_ctx;
 
@@ -103,8 +108,11 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
 #define CK_CLASS_2BIT_LE_65536 (1u << 2)
 #define CK_CLASS_2BIT_LE_425984 (1u << 3)
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes /* 0 for the packed2 entry */);
+/* bytes of the CK_F_ALIGNED_OUT arena of a batch (host and device entries) */
+uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records);
+/* flags: CK_F_NO_BYTES, CK_F_ALIGNED_OUT */
 int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets,
-                         uint32_t n_records, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start,
+                         uint32_t n_records, uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start,
                          uint8_t *out_strand, uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
 /* raw/normalised bytes -> lane formats (the k_prepare step), then canonicalise; out_len is required */
 int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets,

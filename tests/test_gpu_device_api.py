@@ -34,16 +34,25 @@ def _oracle_for(ctx, D, torch, batch, n):
     ("all classes, no promise", 1, 64, 20000, 200, 20, 0, 3000),
     ("short and tiny", 0, 1, 130, 100, 0, 0, 20000),
 ])
-def test_device_path_matches_oracle(env, name, kind, lo, hi, dup, adv, mask, n):
+@pytest.mark.parametrize("aligned", [False, True])
+def test_device_path_matches_oracle(env, name, kind, lo, hi, dup, adv, mask, n, aligned):
     ctx, D, torch = env
     b = D.synth_batch(ctx, seed=11, first_index=0, n_records=n, kind=kind, lo=lo, hi=hi, dup_permille=dup,
                       adversarial_permille=adv)
-    outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True)
+    outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True, aligned=aligned)
     ws = D.Workspace(ctx, n)
     D.canon_packed2(ctx, b, outs, ws, class_mask=mask)
     D.check(ctx, ws)
     ascii_, off, want = _oracle_for(ctx, D, torch, b, n)
-    got_out = outs.out[: b.total].cpu().numpy()
+    if aligned:
+        # record i lives at 16 * ((offsets[i] >> 4) + i): gather it back to the compact layout
+        arena = outs.out.cpu().numpy()
+        starts = ctx.aligned_starts(off).astype(np.int64)
+        lens = (off[1:] - off[:-1]).astype(np.int64)
+        src = np.repeat(starts - off[:-1].astype(np.int64), lens) + np.arange(int(off[-1]), dtype=np.int64)
+        got_out = arena[src]
+    else:
+        got_out = outs.out[: b.total].cpu().numpy()
     assert np.array_equal(got_out, want["out"]), name
     assert np.array_equal(outs.start[:n].cpu().numpy().astype(np.uint32), want["start"]), name
     assert np.array_equal(outs.strand[:n].cpu().numpy(), want["strand"]), name

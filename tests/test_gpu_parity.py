@@ -35,16 +35,22 @@ def _batch(seqs):
     return arena, off
 
 
-def _check_batch(ctx, seqs, normalize, tag=""):
+def _check_batch(ctx, seqs, normalize, tag="", aligned=None):
+    if aligned is None:                       # both output layouts
+        _check_batch(ctx, seqs, normalize, tag + " [same offsets]", False)
+        _check_batch(ctx, seqs, normalize, tag + " [aligned arena]", True)
+        return
     arena, off = _batch(seqs)
     want = oracle.canonicalize_batch(arena, off, normalize=normalize, threads=4)
-    got = ctx.canonicalize_batch(arena, off, normalize=normalize)
+    got = ctx.canonicalize_batch(arena, off, normalize=normalize, aligned=aligned)
+    gstart = ctx.aligned_starts(off) if aligned else off[:-1]
     bad = []
     for i in range(len(seqs)):
         o = int(off[i])
         wl, gl = int(want["lens"][i]), int(got["lens"][i])
         wb = want["out"][o:o + wl].tobytes()
-        gb = got["out"][o:o + gl].tobytes()
+        go = int(gstart[i])
+        gb = got["out"][go:go + gl].tobytes()
         if (wl != gl or wb != gb or int(want["start"][i]) != int(got["start"][i])
                 or int(want["strand"][i]) != int(got["strand"][i]) or int(want["hash"][i]) != int(got["hash"][i])):
             bad.append((i, seqs[i][:80], wb[:60], gb[:60], int(want["start"][i]), int(got["start"][i]),
