@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcirckit_b200.so")
+LIB_PATH = os.environ.get("CIRCKIT_B200_LIB") or os.path.join(HERE, "libcirckit_b200.so")   # env: A/B builds
 
 CK_OK = 0
 CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5

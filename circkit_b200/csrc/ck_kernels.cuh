@@ -253,8 +253,8 @@ struct ClassifyArgs {
     u32 n_records;
     u32 *lists;        // CLS_COUNT lists of n_records entries each
     u32 *counts;       // CLS_COUNT counters (zeroed by the caller)
-    int only_class;    // >= 0: no lists are written (that class runs over all records directly); records of
-                       // any other class are counted in counts[CLS_HUGE] = "left unprocessed"
+    u32 direct_mask;   // != 0: no lists are written (the classes of the mask run over all records directly);
+                       // records of any other class are counted in counts[CLS_HUGE] = "left unprocessed"
 };
 __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
 {
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
         else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
         else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
     }
-    if (a.only_class >= 0) {
-        const u32 m = __ballot_sync(CK_FULL, cls >= 0 && cls != a.only_class);
+    if (a.direct_mask) {
+        const u32 m = __ballot_sync(CK_FULL, cls >= 0 && !((a.direct_mask >> cls) & 1u));
         if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + CLS_HUGE, __popc(m));
         return;
     }

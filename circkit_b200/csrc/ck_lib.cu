@@ -173,7 +173,6 @@ int set_attrs(ck_ctx *ctx)
     if (ctx->attrs_set) return CK_OK;
     int rc;
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
-    if ((rc = set_smem(ctx, k_canon_w2<false>, cls_smem_bytes(CLS_W2M)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
     ctx->attrs_set = true;
@@ -194,16 +193,20 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     int rc = set_attrs(ctx);
     if (rc) return rc;
     CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 16 * sizeof(u32), st));
-    // a promise of exactly one class lets that class index the records directly (no work lists)
+    // a promise of exactly one class lets that class index the records directly (no work lists); the two warp-shaped
+    // 2-bit classes together run as ONE direct launch of the n <= 8192 kernel
     int only = -1;
+    const bool merged = class_mask == ((1u << CLS_W2S) | (1u << CLS_W2M));
     if (class_mask && (class_mask & (class_mask - 1)) == 0)
         for (int c = 0; c < CLS_COUNT; c++) if (class_mask == (1u << c)) only = c;
-    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts, only};
+    if (merged) only = CLS_W2M;
+    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts, only >= 0 ? (merged ? class_mask : (1u << only)) : 0u};
     k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
     ctx->launches++;
     for (int c = 0; c < CLS_COUNT; c++) {
         if (c == CLS_HUGE) continue;
         if (class_mask && !(class_mask & (1u << c))) continue;
+        if (merged && c == CLS_W2S) continue;
         CanonArgs a{};
         a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
         if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
@@ -213,6 +216,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
                 : (c == CLS_C2B) ? cls_max_n(CLS_C2A) + 1 : (c == CLS_C4) ? cls_max_n(CLS_W4) + 1
                 : (c == CLS_C8) ? cls_max_n(CLS_W8) + 1 : (c == CLS_EMPTY ? 0u : 1u);
         if (c == CLS_EMPTY) a.max_n = 0;
+        if (merged) a.min_n = 1;
         a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
         a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
         a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
@@ -224,8 +228,22 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             CK_CUDA(ctx, cudaEventRecord(e0, st));
         }
         switch (c) {
-        case CLS_W2S: k_canon_w2<true><<<grid, thr, smem, st>>>(a); break;
-        case CLS_W2M: k_canon_w2<false><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2S: case CLS_W2M: {
+            // specialised variants for the resident fast path (direct range, both strands, aligned bytes or none)
+            const bool fast = !a.lens && !(a.mode & 1u) && (!a.out || (a.mode & 2u)) && a.out_start && a.out_strand;
+            const int v = fast ? ((a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0)) : -1;
+#define CK_W2(SM, V) k_canon_w2<SM, V><<<grid, thr, smem, st>>>(a)
+#define CK_W2_SWITCH(SM)                                                                                        \
+            switch (v) {                                                                                        \
+            case 0: CK_W2(SM, 0); break; case 1: CK_W2(SM, 1); break; case 2: CK_W2(SM, 2); break;              \
+            case 3: CK_W2(SM, 3); break; case 4: CK_W2(SM, 4); break; case 5: CK_W2(SM, 5); break;              \
+            case 6: CK_W2(SM, 6); break; case 7: CK_W2(SM, 7); break; default: CK_W2(SM, -1);                   \
+            }
+            if (c == CLS_W2S) { CK_W2_SWITCH(true) } else { CK_W2_SWITCH(false) }
+#undef CK_W2_SWITCH
+#undef CK_W2
+            break;
+        }
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
         case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;

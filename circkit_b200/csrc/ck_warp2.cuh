@@ -4,8 +4,8 @@
 // Same answer as ck_record.cuh (the generic path it falls back to for true ties and tiny records).  The
 // kernel is issue-bound (integer ALU pipe: SHF / PRMT / VIMNMX3 issue every other cycle per SM sub-partition,
 // tools/micro/pipes.cu), so every phase is written to a warp-instruction budget:
-//   * staging: one 64-bit load per lane into the shared-memory strand, five circular-extension units,
-//     reverse complement by BREV + pair swap;
+//   * staging: one 64-bit load per lane into the shared-memory strand, three circular-extension units,
+//     reverse complement by BREV + one LOP3;
 //   * scan: 8-mer keys as 16-bit halves; one lane-step covers 32 rotations with 14 funnel shifts and
 //     8 VIMNMX3.U16x2 (each 32-bit window holds the keys of rotations i and i+8); one REDUX per round keeps the
 //     warp minimum, a per-lane round mask remembers where it occurred;
@@ -18,20 +18,38 @@
 //     generation feeds both);
 //   * XXH3-64 (n > 240): lane = (stripe, accumulator pair); the last stripe rides in spare lanes of the
 //     final round; accumulators are reduced across lanes once per 1024-byte block with a transposed butterfly.
+// Shared memory is addressed with 32-bit shared-window addresses (ld.shared / st.shared) to keep address
+// arithmetic to one instruction per access.
 #pragma once
 #include "ck_kernels.cuh"
 
 namespace ck {
 
-// 16 bases starting at position q (< n) of strand X, as 32 bits
-__device__ __forceinline__ u32 w2_window(const u32 *X, u32 q)
+// ---- shared memory by 32-bit address
+__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64(u32 a)
 {
-    const u32 j = q >> 4;
-    return __funnelshift_l(X[j + 1], X[j], 2u * q);           // shift taken mod 32
+    uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(u32 a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+
+// 16 bases starting at position q of the strand whose unit 0 sits at shared address xb
+__device__ __forceinline__ u32 w2_win(u32 xb, u32 q)
+{
+    const u32 a = xb + ((q >> 4) << 2);
+    const u32 hi = lds32(a), lo = lds32(a + 4);
+    return __funnelshift_l(lo, hi, q + q);                        // shift taken mod 32
+}
+// reverse complement of 16 packed bases: reverse the bit order, swap the two bits of every pair back, complement
+__device__ __forceinline__ u32 w2_revcomp(u32 x)
+{
+    const u32 r = __brev(x);
+    u32 o;
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1b;" : "=r"(o) : "r"(r >> 1), "r"(r + r));    // ~((a & c) | (b & ~c))
+    return o;
 }
 
-// ---- unaligned output (same offsets as the input): destination-aligned chunks with ragged record edges
-struct W2Lut { const u32 *Xf; };
 __device__ __forceinline__ uint4 w2_ascii16(u32 w)
 {
     const u32 T = 0x54474341u;                                // 'A','C','G','T'
@@ -46,7 +64,8 @@ __device__ __forceinline__ uint4 w2_ascii16(u32 w)
     v.w = __byte_perm(pe_lo, po_lo, 0x0415);                  // bases 12..15
     return v;
 }
-__device__ __forceinline__ void w2_emit_ragged(const u32 *X, u32 n, u32 start, u8 *dst)
+// unaligned output (same offsets as the input): destination-aligned chunks with ragged record edges
+__device__ __noinline__ void w2_emit_ragged(u32 xb, u32 n, u32 start, u8 *dst)
 {
     const u32 lane = lane_id();
     const u32 a = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
@@ -55,7 +74,7 @@ __device__ __forceinline__ void w2_emit_ragged(const u32 *X, u32 n, u32 start, u
         const int t0 = (int)(16u * c) - (int)a;               // record-relative byte of this chunk's first byte
         u32 q = start + (u32)(t0 < 0 ? t0 + (int)n : t0);     // n >= 128 here, so one wrap suffices
         if (q >= n) q -= n;
-        const uint4 v = w2_ascii16(w2_window(X, q));
+        const uint4 v = w2_ascii16(w2_win(xb, q));
         store_chunk(dst, t0, n, ((u64)v.y << 32) | v.x, ((u64)v.w << 32) | v.z);
     }
 }
@@ -80,19 +99,13 @@ __device__ __forceinline__ u32 w2_step_min16(u32 x0, u32 x1, u32 x2)
 struct W2Const {
     u64 sec[24];        // secret as LE u64 at byte offsets 8 i        (stripe keys, scramble keys = sec[16 + i])
     u64 lastsec[8];     // LE u64 at byte offsets 121 + 8 i            (last stripe: secret + 192 - 64 - 7)
-};                      // lastsec must follow sec directly: the hash indexes both through one base pointer
+};                      // lastsec must follow sec directly: the hash indexes both through one base address
 __device__ __forceinline__ void w2_fill_const(W2Const *K)
 {
     const u32 t = threadIdx.x;
     if (t < 24) K->sec[t] = sec64(8 * (int)t);
     else if (t < 32) K->lastsec[t - 24] = sec64(121 + 8 * (int)(t - 24));
 }
-
-struct W2Hash {
-    u64 init;           // initial accumulator of this lane's accumulator index
-    u64 scr;            // scramble key  (secret + 128 + 8 idx)
-    u64 mrg;            // merge key     (secret + 11 + 8 idx)
-};
 // lane -> accumulator index it owns after a block reduction: pair k = lane & 3, bit 2 of the lane picks 2k or 2k+1
 __device__ __forceinline__ u32 w2_acc_index(u32 lane) { return 2u * (lane & 3u) + ((lane >> 2) & 1u); }
 
@@ -109,160 +122,257 @@ __device__ __forceinline__ u64 w2_reduce_pair(u64 a0, u64 a1, u32 lane)
     return keep;
 }
 
+// slow paths, kept out of line so the common path stays small; results come back packed as (start << 1) | strand
+__device__ __noinline__ u32 w2_slow_start(u32 *Xf, u32 *Xr, u32 n, u32 xb, u32 *scr)
+{
+    // the duel path reads two more extension units than the scan: build units jn+3, jn+4 of both strands
+    const u32 lane = lane_id(), jn = n >> 4, rem = n & 15u;
+    const u32 stride = (u32)(Xr - Xf);
+    if (lane < 2) sts32(xb + 4 * (jn + 3 + lane), w2_win(xb, 16u * (3 + lane) - rem));
+    __syncwarp();
+    if (lane < 2) {
+        int t = (int)n - 16 * (int)(jn + 4 + lane);
+        if (t < 0) t += (int)n;
+        sts32(xb + 4 * (stride + jn + 3 + lane), w2_revcomp(w2_win(xb, (u32)t)));
+    }
+    __syncwarp();
+    const RecordOut o = canonical_start<2, Grp<false> >(Xf, Xr, n, scr, nullptr, false);
+    return (o.start << 1) | o.strand;
+}
+__device__ __noinline__ u32 w2_tiny_record(const u64 *src, u32 n, u8 *dst, u32 *Xf, u32 *Xr, u32 *scr, bool fwd_only)
+{
+    typedef Grp<false> G;
+    RecordIn in; in.packed2 = src; in.bytes = nullptr; in.n = n;
+    stage_record<2, G>(in, Xf, Xr);
+    const RecordOut o = canonical_start<2, G>(Xf, Xr, n, scr, nullptr, fwd_only);
+    const u32 *X = o.strand ? Xr : Xf;
+    if (dst) emit_ascii<2, G>(X, n, o.start, dst);
+    return (o.start << 1) | o.strand;
+}
+__device__ __noinline__ u64 w2_short_hash(const u32 *X, u32 n, u32 start) { return xxh3_short_warp<2>(X, n, start); }
+__device__ __noinline__ u64 w2_any_hash(const u32 *X, u32 n, u32 start) { return xxh3_canonical<2, Grp<false> >(X, n, start, nullptr, nullptr); }
+
+// Kernel variants.  V < 0: every option is read from CanonArgs at run time (normalised lengths, forward-only
+// library calls, either output layout, optional outputs).  V >= 0: packed lengths from the offsets, both strands,
+// out_start / out_strand present; bit 0 = XXH3-64 wanted, bit 1 = canonical bytes wanted in the aligned arena (else
+// no bytes), bit 2 = records come from a work list (else the direct range [0, n_direct)).
 // SMALL: every record of the launch has n <= 512 (one scan round, one staging pass); otherwise n <= 8192.
-template <bool SMALL>
-__global__ void __launch_bounds__(256) k_canon_w2(CanonArgs a)
+#define CK_W2_HASH 1
+#define CK_W2_OUT 2
+#define CK_W2_LIST 4
+template <bool SMALL, int V>
+__global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
 {
     extern __shared__ __align__(16) u32 smem[];
-    typedef Grp<false> G;
     W2Const *K = reinterpret_cast<W2Const *>(smem);
     w2_fill_const(K);
     __syncthreads();
+    constexpr bool RT = V < 0;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 stride = a.smem_units;                              // even, so both strands stay 8-byte aligned
     u32 *Xf = smem + sizeof(W2Const) / 4 + (size_t)wid * 2 * stride, *Xr = Xf + stride;
+    const u32 kb = (u32)__cvta_generic_to_shared(smem);           // W2Const
+    const u32 xf = (u32)__cvta_generic_to_shared(Xf), xr = xf + 4 * stride;
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
-    const u32 count = a.list ? *a.count : a.n_direct;
-    const bool fwd_only = (a.mode & 1u) != 0;
-    const bool aligned_out = (a.mode & 2u) != 0;
+    const bool use_list = RT ? a.list != nullptr : (V & CK_W2_LIST) != 0;
+    const u32 count = use_list ? *a.count : a.n_direct;
+    const bool fwd_only = RT && (a.mode & 1u) != 0;
+    const bool aligned_out = RT ? (a.mode & 2u) != 0 : true;
+    const bool want_hash = RT ? a.out_hash != nullptr : (V & CK_W2_HASH) != 0;
+    const bool want_out = RT ? a.out != nullptr : (V & CK_W2_OUT) != 0;
     const u32 aidx = w2_acc_index(lane);
-    W2Hash hc;
-    hc.init = xxh3_init_acc(aidx);
-    hc.scr = K->sec[16 + aidx];
-    hc.mrg = sec64(11 + 8 * (int)aidx);
-    const u64 *ksec = K->sec;
+    u64 h_init = 0, h_scr = 0, h_mrg = 0;
+    if (want_hash) { h_init = xxh3_init_acc(aidx); h_scr = K->sec[16 + aidx]; h_mrg = sec64(11 + 8 * (int)aidx); }
 
-    for (u32 e = gw; e < count; e += nw) {
-        const u32 rec = a.list ? a.list[e] : e;
-        const u64 off = a.offsets[rec];
-        const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
-        if (a.list == nullptr && (n < a.min_n || n > a.max_n)) continue;  // direct mode: k_classify reported it
+    // software pipeline: the offsets (and, in direct mode, the first packed word of every lane) of the next record are
+    // requested while the current one is processed, so neither DRAM round trip sits on the critical path
+    u32 e = gw;
+    u32 rec_n = 0, rec_nn = 0; u64 off_n = 0; u32 end_n = 0; uint2 d_n = make_uint2(0, 0);
+    const bool pipelined = !RT;
+    // the next record's packed words are requested once its offsets have had time to arrive (after the staging phases)
+#define CK_W2_PREFETCH_DATA()                                                                                        \
+    do {                                                                                                             \
+        if (pipelined && e + nw < count) {                                                                           \
+            const u32 nn = end_n - (u32)off_n;                                                                       \
+            if (lane < ((nn + 31) >> 5))                                                                             \
+                d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + ((off_n >> 5) + rec_n)) + lane);             \
+        }                                                                                                            \
+    } while (0)
+    if (pipelined && e < count) {
+        rec_n = use_list ? a.list[e] : e;
+        if (use_list && e + nw < count) rec_nn = a.list[e + nw];
+        off_n = a.offsets[rec_n]; end_n = (u32)a.offsets[rec_n + 1];
+        const u32 nn = end_n - (u32)off_n;
+        if (lane < ((nn + 31) >> 5)) d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + ((off_n >> 5) + rec_n)) + lane);
+    }
+    for (; e < count; e += nw) {
+        u32 rec; u64 off; u32 n; uint2 d0 = make_uint2(0, 0);
+        if (pipelined) {
+            rec = rec_n; off = off_n; n = end_n - (u32)off_n; d0 = d_n;
+            const u32 e2 = e + nw;
+            if (e2 < count) {
+                rec_n = use_list ? rec_nn : e2;                       // list entries are fetched two records ahead
+                if (use_list && e2 + nw < count) rec_nn = a.list[e2 + nw];
+                off_n = a.offsets[rec_n]; end_n = (u32)a.offsets[rec_n + 1];
+            }
+        } else {
+            rec = use_list ? a.list[e] : e;
+            off = a.offsets[rec];
+            n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
+        }
+        const bool in_range = use_list || (n >= a.min_n && n <= a.max_n);    // direct mode: k_classify reported the rest
         const u64 *src = a.packed2 + ((off >> 5) + rec);
-        u8 *dst = a.out ? a.out + (aligned_out ? 16ull * ((off >> 4) + rec) : off) : nullptr;
-        RecordOut o;
+        u8 *dst = want_out ? a.out + (aligned_out ? 16ull * ((off >> 4) + rec) : off) : nullptr;
+        u32 os = 0;                                               // (start << 1) | strand of the canonical rotation
         u64 h = 0;
-        if (n < 128 || fwd_only) {
+        if (!in_range) {
+            CK_W2_PREFETCH_DATA();
+        } else if (n < 128 || fwd_only) {
             // tiny records and the forward-only library calls: generic path
-            RecordIn in; in.packed2 = src; in.bytes = nullptr; in.n = n;
-            stage_record<2, G>(in, Xf, Xr);
-            o = canonical_start<2, G>(Xf, Xr, n, scr, nullptr, fwd_only);
-            const u32 *X = o.strand ? Xr : Xf;
-            if (dst) emit_ascii<2, G>(X, n, o.start, dst);
-            if (a.out_hash) h = xxh3_canonical<2, G>(X, n, o.start, nullptr, nullptr);
+            os = w2_tiny_record(src, n, dst, Xf, Xr, scr, fwd_only);
+            if (want_hash) h = w2_any_hash((os & 1u) ? Xr : Xf, n, os >> 1);
+            CK_W2_PREFETCH_DATA();
         } else {
             const u32 jn = n >> 4, rem = n & 15u;
             // ---- stage the forward strand
             {
                 const u32 W = (n + 31) >> 5;
-                if (SMALL) {
-                    if (lane < W) *reinterpret_cast<uint2 *>(Xf + 2 * lane) = __ldg(reinterpret_cast<const uint2 *>(src) + lane);
+                if (pipelined) {
+                    if (lane < W) sts64(xf + 8 * lane, d0);
+                    if (!SMALL) {
+#pragma unroll 1
+                        for (u32 k = lane + 32; k < W; k += 32) sts64(xf + 8 * k, __ldg(reinterpret_cast<const uint2 *>(src) + k));
+                    }
                 } else {
-                    for (u32 k = lane; k < W; k += 32)
-                        *reinterpret_cast<uint2 *>(Xf + 2 * k) = __ldg(reinterpret_cast<const uint2 *>(src) + k);
+#pragma unroll 1
+                    for (u32 k = lane; k < W; k += 32) sts64(xf + 8 * k, __ldg(reinterpret_cast<const uint2 *>(src) + k));
                 }
             }
             __syncwarp();
-            if (lane < 5) {                                       // circular extension: units jn .. jn + 4
+            if (lane < 3) {                                       // circular extension: units jn .. jn + 2
                 u32 val;
-                if (lane == 0) {
-                    const u32 g0 = Xf[0];
-                    val = rem ? ((Xf[jn] & ~(0xffffffffu >> (2 * rem))) | (g0 >> (2 * rem))) : g0;
-                } else {
-                    val = w2_window(Xf, 16u * lane - rem);        // (jn + lane) * 16 - n; reads units < jn (n >= 128)
-                }
-                Xf[jn + lane] = val;
+                if (lane == 0) val = (lds32(xf + 4 * jn) & ~(0xffffffffu >> (2 * rem))) | (lds32(xf) >> (2 * rem));
+                else val = w2_win(xf, 16u * lane - rem);          // (jn + lane) * 16 - n; reads units < jn (n >= 128)
+                sts32(xf + 4 * (jn + lane), val);
             }
             __syncwarp();
-            // ---- reverse complement strand, units 0 .. jn + 4
-            for (u32 j = lane; j < jn + 5; j += 32) {
+            // ---- reverse complement strand, units 0 .. jn + 2
+#pragma unroll 1
+            for (u32 j = lane; j < jn + 3; j += 32) {
                 int t = (int)n - 16 * (int)(j + 1);
                 if (t < 0) t += (int)n;
-                Xr[j] = revcomp2_u32(w2_window(Xf, (u32)t));
+                sts32(xr + 4 * j, w2_revcomp(w2_win(xf, (u32)t)));
             }
             __syncwarp();
+            CK_W2_PREFETCH_DATA();
             // ---- scan: minimal 8-mer over the 2n rotations; step t < S: forward units (2t, 2t+1), else reverse
             const u32 S = (n + 31) >> 5, T2 = 2 * S;
-            u32 gbest = 0xffffffffu, rmask = 0;
-            {
-                u32 r = 0;
-                for (u32 t = lane; (SMALL ? r < 1 : 32 * r < T2); t += 32, r++) {
-                    u32 mm = 0x10000u;
-                    if (t < T2) {
-                        const u32 u = t >= S ? t - S : t;
-                        const u32 *p = Xf + (t >= S ? stride : 0u) + 2 * u;
-                        const uint2 x01 = *reinterpret_cast<const uint2 *>(p);
-                        const u32 m = w2_step_min16(x01.x, x01.y, p[2]);
-                        mm = min(m >> 16, m & 0xffffu);
+            const u32 xrs = xr - 8 * S;                           // step t >= S reads reverse units 2 (t - S)
+            u32 cnt = 0, best = 0;
+            if (SMALL) {
+                const u32 tt = min(lane, T2 - 1);
+                const u32 p = (tt >= S ? xrs : xf) + 8 * tt;
+                const uint2 x01 = lds64(p);
+                const u32 m = w2_step_min16(x01.x, x01.y, lds32(p + 8));
+                const u32 mm = lane < T2 ? min(m >> 16, m & 0xffffu) : 0x10000u;
+                const u32 gbest = __reduce_min_sync(CK_FULL, mm);
+                u32 cand = __ballot_sync(CK_FULL, mm == gbest);
+                // resolve: re-read the step(s) holding the minimal 8-mer, one rotation per lane, as 16-mers
+                u32 best32 = 0xffffffffu;
+                do {
+                    const u32 L = 31u - __clz(cand);
+                    cand ^= 1u << L;
+                    const u32 strand = L >= S ? 1u : 0u;
+                    const u32 p0 = 32 * (strand ? L - S : L);
+                    const u32 w = w2_win(strand ? xr : xf, p0 + lane);
+                    const bool hit = (w >> 16) == gbest && p0 + lane < n;
+                    const u32 hits = __ballot_sync(CK_FULL, hit);
+                    if (cand == 0 && cnt == 0 && hits != 0 && (hits & (hits - 1)) == 0) {     // the common case: one step, one rotation
+                        cnt = 1; best = ((p0 + 31u - __clz(hits)) << 1) | strand;
+                        break;
                     }
+                    const u32 wv = hit ? w : 0xffffffffu;
+                    const u32 g32 = __reduce_min_sync(CK_FULL, wv);
+                    const u32 hb = __ballot_sync(CK_FULL, hit && wv == g32);
+                    if (g32 < best32) { best32 = g32; cnt = 0; }
+                    if (g32 == best32 && hb) { cnt += __popc(hb); best = ((p0 + 31u - __clz(hb)) << 1) | strand; }
+                } while (cand);
+            } else {
+                u32 gbest = 0xffffffffu, rmask = 0, r = 0;
+#pragma unroll 1
+                for (u32 t = lane; 32 * r < T2; t += 32, r++) {
+                    const u32 tt = min(t, T2 - 1);
+                    const u32 p = (tt >= S ? xrs : xf) + 8 * tt;
+                    const uint2 x01 = lds64(p);
+                    const u32 m = w2_step_min16(x01.x, x01.y, lds32(p + 8));
+                    const u32 mm = t < T2 ? min(m >> 16, m & 0xffffu) : 0x10000u;
                     const u32 g = __reduce_min_sync(CK_FULL, mm);
                     if (g < gbest) { gbest = g; rmask = 0; }
                     if (mm == gbest) rmask |= 1u << r;
                 }
+                u32 best32 = 0xffffffffu;
+#pragma unroll 1
+                for (u32 any = __ballot_sync(CK_FULL, rmask != 0); any; any = __ballot_sync(CK_FULL, rmask != 0)) {
+                    const u32 L = 31u - __clz(any);
+                    const u32 mL = __shfl_sync(CK_FULL, rmask, L);
+                    const u32 rr = 31u - __clz(mL);
+                    if (lane == L) rmask ^= 1u << rr;
+                    const u32 t = L + 32 * rr;
+                    const u32 strand = t >= S ? 1u : 0u;
+                    const u32 p0 = 32 * (strand ? t - S : t);
+                    const u32 w = w2_win(strand ? xr : xf, p0 + lane);
+                    const bool hit = (w >> 16) == gbest && p0 + lane < n;
+                    const u32 wv = hit ? w : 0xffffffffu;
+                    const u32 g32 = __reduce_min_sync(CK_FULL, wv);
+                    const u32 hb = __ballot_sync(CK_FULL, hit && wv == g32);
+                    if (g32 < best32) { best32 = g32; cnt = 0; }
+                    if (g32 == best32 && hb) { cnt += __popc(hb); best = ((p0 + 31u - __clz(hb)) << 1) | strand; }
+                }
             }
-            // ---- resolve: every step that holds the minimal 8-mer is re-read, one rotation per lane, as 16-mers
-            u32 best32 = 0xffffffffu, cnt = 0, bestpos = 0, beststrand = 0;
-            for (u32 any = __ballot_sync(CK_FULL, rmask != 0); any; any = __ballot_sync(CK_FULL, rmask != 0)) {
-                const u32 L = __ffs(any) - 1;
-                const u32 mL = __shfl_sync(CK_FULL, rmask, L);
-                const u32 r = __ffs(mL) - 1;
-                if (lane == L) rmask &= rmask - 1;
-                const u32 t = L + 32 * r;
-                const u32 strand = t >= S ? 1u : 0u;
-                const u32 p = 32 * (strand ? t - S : t) + lane;
-                const u32 w = w2_window(strand ? Xr : Xf, p);
-                const bool hit = (w >> 16) == gbest && p < n;
-                const u32 wv = hit ? w : 0xffffffffu;
-                const u32 g32 = __reduce_min_sync(CK_FULL, wv);
-                const u32 hb = __ballot_sync(CK_FULL, hit && wv == g32);
-                if (g32 < best32) { best32 = g32; cnt = 0; }
-                if (g32 == best32 && hb) { cnt += __popc(hb); bestpos = p - lane + (__ffs(hb) - 1); beststrand = strand; }
-            }
-            if (cnt == 1) {
-                o.start = bestpos; o.strand = beststrand;
-            } else {
-                // equal minimal 16-mers (repeats, multimers, palindromic circles): duel-based generic path
-                o = canonical_start<2, G>(Xf, Xr, n, scr, nullptr, false);
-            }
-            const u32 *X = o.strand ? Xr : Xf;
+            // equal minimal 16-mers (repeats, multimers, palindromic circles): duel-based generic path
+            os = cnt == 1 ? best : w2_slow_start(Xf, Xr, n, xf, scr);
+            const u32 start = os >> 1;
+            const u32 xs = (os & 1u) ? xr : xf;
             // ---- canonical ASCII (+ XXH3-64 of it)
-            const bool long_hash = a.out_hash != nullptr && n > 240;
-            if (dst && !aligned_out) w2_emit_ragged(X, n, o.start, dst);
-            if ((dst && aligned_out) || long_hash) {
+            const bool long_hash = want_hash && n > 240;
+            const bool store = dst && aligned_out;
+            if (RT && dst && !aligned_out) w2_emit_ragged(xs, n, start, dst);
+            if (store || long_hash) {
                 const u32 nchunks = (n + 15) >> 4;
                 const u32 vbase = (nchunks + 3u) & ~3u;               // last-stripe chunks: 4 spare lanes after the data
                 const u32 cend = long_hash ? vbase + 4 : nchunks;
                 const u32 nfull = (n - 1) >> 6;                       // stripes consumed by the stripe loop
                 const u32 nb_blocks = (n - 1) >> 10;
-                const bool store = dst && aligned_out;
-                u64 base = hc.init, acc0 = 0, acc1 = 0;
+                u64 base = h_init, acc0 = 0, acc1 = 0;
                 u32 r = 0;
+#pragma unroll 1
                 for (u32 c = lane; 32 * r < cend; c += 32, r++) {
-                    if (c < cend) {
-                        const bool last = c >= vbase;
-                        u32 q = o.start + (last ? n - 64 + 16 * (c - vbase) : 16 * c);
-                        if (q >= n) q -= n;
-                        const uint4 v = w2_ascii16(w2_window(X, q));
-                        if (store && c < nchunks) *reinterpret_cast<uint4 *>(dst + 16 * (size_t)c) = v;
-                        if (long_hash) {
-                            const u32 s = c >> 2;
-                            const u32 sidx = last ? 24 + 2 * (c - vbase) : (s & 15u) + 2 * (c & 3u);
-                            if (last || s < nfull) {
-                                const u64 d0 = ((u64)v.y << 32) | v.x, d1 = ((u64)v.w << 32) | v.z;
-                                const u64 k0 = d0 ^ ksec[sidx], k1 = d1 ^ ksec[sidx + 1];
-                                acc0 += (u64)(u32)k0 * (u64)(u32)(k0 >> 32) + d1;
-                                acc1 += (u64)(u32)k1 * (u64)(u32)(k1 >> 32) + d0;
-                            }
+                    const u32 cc = min(c, cend - 1);                  // spare lanes repeat the last chunk (same bytes, same address)
+                    const bool last = long_hash && cc >= vbase;
+                    u32 q = start + (last ? n - 64 + 16 * (cc - vbase) : 16 * cc);
+                    if (q >= n) q -= n;
+                    const uint4 v = w2_ascii16(w2_win(xs, q));
+                    if (store && cc < nchunks) *reinterpret_cast<uint4 *>(dst + 16 * (size_t)cc) = v;
+                    if (long_hash) {
+                        const u32 s = cc >> 2;
+                        const u32 sidx = last ? 24 + 2 * (cc - vbase) : (s & 15u) + 2 * (cc & 3u);
+                        if (c < cend && (last || s < nfull)) {
+                            const u64 d0v = ((u64)v.y << 32) | v.x, d1v = ((u64)v.w << 32) | v.z;
+                            const uint2 s0 = lds64(kb + 8 * sidx), s1 = lds64(kb + 8 * sidx + 8);
+                            const u32 k0l = v.x ^ s0.x, k0h = v.y ^ s0.y, k1l = v.z ^ s1.x, k1h = v.w ^ s1.y;
+                            acc0 += (u64)k0l * (u64)k0h + d1v;
+                            acc1 += (u64)k1l * (u64)k1h + d0v;
                         }
                     }
-                    if (long_hash && (r & 1u) && (r >> 1) < nb_blocks) {      // a 1024-byte block is complete
+                    if (long_hash && !SMALL && (r & 1u) && (r >> 1) < nb_blocks) {      // a 1024-byte block is complete
                         u64 t = base + w2_reduce_pair(acc0, acc1, lane);
-                        t ^= t >> 47; t ^= hc.scr; t *= CK_P32_1;
+                        t ^= t >> 47; t ^= h_scr; t *= CK_P32_1;
                         base = t; acc0 = 0; acc1 = 0;
                     }
                 }
                 if (long_hash) {
-                    const u64 keyed = (base + w2_reduce_pair(acc0, acc1, lane)) ^ hc.mrg;    // acc[aidx] ^ secret[11 + 8 aidx]
+                    const u64 keyed = (base + w2_reduce_pair(acc0, acc1, lane)) ^ h_mrg;    // acc[aidx] ^ secret[11 + 8 aidx]
                     const u64 partner = __shfl_xor_sync(CK_FULL, keyed, 4);
                     u64 term = lane < 4 ? mul128_fold64(keyed, partner) : 0ULL;
                     term += __shfl_xor_sync(CK_FULL, term, 1);
@@ -270,15 +380,18 @@ __global__ void __launch_bounds__(256) k_canon_w2(CanonArgs a)
                     h = xxh3_avalanche((u64)n * CK_P64_1 + term);                            // valid in lanes 0..3
                 }
             }
-            if (a.out_hash && n <= 240) h = xxh3_short_warp<2>(X, n, o.start);
+            if (want_hash && n <= 240) h = w2_short_hash((os & 1u) ? Xr : Xf, n, start);
         }
-        if (lane == 0) {
-            if (a.out_start) a.out_start[rec] = o.strand ? (n - 1 - o.start) : o.start;
-            if (a.out_strand) a.out_strand[rec] = (u8)o.strand;
-            if (a.out_hash) a.out_hash[rec] = h;
+        if (lane == 0 && in_range) {
+            const u32 start = os >> 1, strand = os & 1u;
+            if (!RT || a.out_start) a.out_start[rec] = strand ? (n - 1 - start) : start;
+            if (!RT || a.out_strand) a.out_strand[rec] = (u8)strand;
+            if (want_hash) a.out_hash[rec] = h;
         }
         __syncwarp();
     }
 }
+
+#undef CK_W2_PREFETCH_DATA
 
 }  // namespace ck
