@@ -39,7 +39,11 @@ def line_map(kernel_pat: str, lib: str = LIB):
             if m:
                 cur = m.group(1) if re.search(kernel_pat, m.group(1)) else None
                 if cur:
-                    out[cur] = {}
+                    # out-of-line device functions ($kernel$callee) share the kernel's section and address space
+                    sub = re.match(r"\$([^$]+)\$", cur)
+                    if sub:
+                        cur = sub.group(1)
+                    out.setdefault(cur, {})
                 continue
             if cur is None:
                 continue
