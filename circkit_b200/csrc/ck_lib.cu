@@ -11,6 +11,7 @@
 #include "../../include/circkit_b200.h"
 #include "ck_kernels.cuh"
 #include "ck_warp2.cuh"
+#include "ck_lane2.cuh"
 #include "ck_synth.cuh"
 
 using namespace ck;
@@ -175,6 +176,11 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
+    const u32 t2s = 8u * t2_warp_bytes<36>();
+    if ((rc = set_smem(ctx, k_canon_t2<36, 0>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 1>, t2s)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 2>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 3>, t2s)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 4>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 5>, t2s)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 6>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 7>, t2s))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -196,7 +202,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     // a promise of exactly one class lets that class index the records directly (no work lists); the two warp-shaped
     // 2-bit classes together run as ONE direct launch of the n <= 8192 kernel
     int only = -1;
-    const bool merged = class_mask == ((1u << CLS_W2S) | (1u << CLS_W2M));
+    const bool merged = false;     // every class runs its own kernel (the n <= 512 class has the lane-per-record kernel)
     if (class_mask && (class_mask & (class_mask - 1)) == 0)
         for (int c = 0; c < CLS_COUNT; c++) if (class_mask == (1u << c)) only = c;
     if (merged) only = CLS_W2M;
@@ -239,7 +245,16 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             case 3: CK_W2(SM, 3); break; case 4: CK_W2(SM, 4); break; case 5: CK_W2(SM, 5); break;              \
             case 6: CK_W2(SM, 6); break; case 7: CK_W2(SM, 7); break; default: CK_W2(SM, -1);                   \
             }
-            if (c == CLS_W2S) { CK_W2_SWITCH(true) } else { CK_W2_SWITCH(false) }
+            if (c == CLS_W2S && v >= 0) {
+                // lane-per-record kernel: 3 CTAs of 8 warps per SM, one tile of 32 rows per warp
+                const u32 g2 = 3u * (u32)ctx->num_sms, sm2 = 8u * t2_warp_bytes<36>();
+#define CK_T2(V) k_canon_t2<36, V><<<g2, 256, sm2, st>>>(a)
+                switch (v) {
+                case 0: CK_T2(0); break; case 1: CK_T2(1); break; case 2: CK_T2(2); break; case 3: CK_T2(3); break;
+                case 4: CK_T2(4); break; case 5: CK_T2(5); break; case 6: CK_T2(6); break; default: CK_T2(7);
+                }
+#undef CK_T2
+            } else if (c == CLS_W2S) { CK_W2_SWITCH(true) } else { CK_W2_SWITCH(false) }
 #undef CK_W2_SWITCH
 #undef CK_W2
             break;
@@ -387,6 +402,12 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     fill_tables(t, secret);
     CK_INIT(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
     CK_INIT(cudaMemcpyToSymbol(c_secret, secret, sizeof(secret)));
+    {
+        u64 last[8], merge[8];
+        for (int i = 0; i < 8; i++) { memcpy(&last[i], secret + 121 + 8 * i, 8); memcpy(&merge[i], secret + 11 + 8 * i, 8); }
+        CK_INIT(cudaMemcpyToSymbol(c_lastsec, last, sizeof(last)));
+        CK_INIT(cudaMemcpyToSymbol(c_mergesec, merge, sizeof(merge)));
+    }
     if (alloc_scratch(ctx, ctx->dev_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
     const u64 B = cfg->max_batch_bytes, R = cfg->max_batch_records;
     if (B || R) {
