@@ -44,11 +44,24 @@ __device__ __forceinline__ void sts128(u32 a, uint4 v)
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// per-warp shared memory: the tile (32 rows of ROWU units) followed by a 2560-byte area that holds the staging
-// descriptors first and the output stage later
+// per-warp shared memory: two tiles (32 rows of ROWU units each; one is computed on while cp.async fills the other),
+// a 2560-byte area that holds the staging descriptors first and the output stage later, the (offset, end) pairs of the
+// two batches in flight, and (work-list launches) the record indices of three batches
 #define CK_T2_AUX_BYTES 2560u
-template <int ROWU> __host__ __device__ constexpr u32 t2_warp_bytes() { return 32u * ROWU * 4u + CK_T2_AUX_BYTES; }
+template <int ROWU> __host__ __device__ constexpr u32 t2_tile_bytes() { return 32u * ROWU * 4u; }
+template <int ROWU> __host__ __device__ constexpr u32 t2_warp_bytes(bool list)
+{
+    return 2u * t2_tile_bytes<ROWU>() + CK_T2_AUX_BYTES + 1024u + (list ? 384u : 0u);
+}
 template <int ROWU> __host__ __device__ constexpr u32 t2_max_n() { return 16u * (ROWU - 4); }
+// warps per CTA: as many as three (short rows) CTAs per SM can hold in 227 KB
+template <int ROWU> __host__ __device__ constexpr u32 t2_warps(bool list) { return ROWU <= 36 ? (list ? 5u : 6u) : 1u; }
+
+__device__ __forceinline__ void cp_async8(u32 dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // 16 canonical letters from a 16-base window; T = letter table, (sa, sb) = interleave selectors.  Forward strand:
 // ("ACGT", 0x2637, 0x0415).  Reverse strand: the window is rotated by 16 bits first and ("TGCA", 0x5140, 0x7362)
@@ -88,66 +101,117 @@ __device__ __forceinline__ void t2_acc16(u64 &a0, u64 &a1, uint4 v, u64 k0, u64 
 }
 
 template <int ROWU, int V>
-__global__ void __launch_bounds__(256, (ROWU <= 36 ? 3 : 1)) k_canon_t2(CanonArgs a)
+__global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), (ROWU <= 36 ? 3 : 1)) k_canon_t2(CanonArgs a)
 {
     extern __shared__ __align__(16) u32 smem[];
     constexpr bool want_hash = (V & CK_W2_HASH) != 0, want_out = (V & CK_W2_OUT) != 0, use_list = (V & CK_W2_LIST) != 0;
-    constexpr u32 WB = t2_warp_bytes<ROWU>(), NMAX = t2_max_n<ROWU>();
+    constexpr u32 TB = t2_tile_bytes<ROWU>(), WB = t2_warp_bytes<ROWU>(use_list), NMAX = t2_max_n<ROWU>();
     constexpr bool BLOCKS = NMAX > 1024;                           // XXH3 block scrambles can occur
     const u32 lane = lane_id(), wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const u32 wsm = (u32)__cvta_generic_to_shared(smem) + wid * WB;  // this warp's tile
-    const u32 tb = wsm + 4u * ROWU * lane;                         // this lane's row
-    const u32 aux = wsm + 128u * ROWU;                             // descriptors / output stage
-    u32 *Xf = smem + (size_t)wid * (WB / 4), *Xr = Xf + a.smem_units;   // generic path: linear strands over the tile
+    const u32 wsm = (u32)__cvta_generic_to_shared(smem) + wid * WB;  // this warp's tiles
+    const u32 aux = wsm + 2u * TB;                                 // descriptors / output stage
+    const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
+    const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
     const u32 count = use_list ? *a.count : a.n_direct;
+    const u32 bstride = nw * 32u;
 
-    for (u32 b = gw * 32u; b < count; b += nw * 32u) {
+    // request the (offset, end) pair of record `rec` into slot `slot`
+    auto fetch_offsets = [&](u32 rec, u32 slot) {
+        cp_async8(offs + 512u * slot, a.offsets + rec);
+        cp_async8(offs + 512u * slot + 8u, a.offsets + rec + 1);
+    };
+    // request the packed words of a batch into tile `tile`: descriptors, then the warp copies record after record
+    auto fetch_tile = [&](u32 tile, u32 rec, u64 off, u32 n, bool want) {
+        const u64 sp = reinterpret_cast<u64>(a.packed2 + ((off >> 5) + rec));
+        sts128(aux + 16u * lane, make_uint4((u32)sp, (u32)(sp >> 32), want ? (n + 31) >> 5 : 0u, 0u));
+        __syncwarp();
+        const u32 tw = wsm + tile * TB;
+        if (ROWU <= 36) {                                          // <= 16 words per record: two records per pass
+            const u32 hlf = lane >> 4, k = lane & 15u;
+#pragma unroll 4
+            for (u32 i = 0; i < 16; i++) {
+                const u32 r = 2 * i + hlf;
+                const uint4 d = lds128(aux + 16u * r);
+                if (k < d.z) cp_async8(tw + 4u * ROWU * r + 8u * k, reinterpret_cast<const uint2 *>(((u64)d.y << 32) | d.x) + k);
+            }
+        } else {
+#pragma unroll 1
+            for (u32 r = 0; r < 32; r++) {
+                const uint4 d = lds128(aux + 16u * r);
+                const uint2 *p = reinterpret_cast<const uint2 *>(((u64)d.y << 32) | d.x);
+#pragma unroll 1
+                for (u32 k = lane; k < d.z; k += 32) cp_async8(tw + 4u * ROWU * r + 8u * k, p + k);
+            }
+        }
+        __syncwarp();
+    };
+    auto is_fast = [&](bool have, u32 n) {
+        const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
+        return in_class && n >= (want_hash ? 241u : 128u) && n <= NMAX;
+    };
+
+    // ---- prologue: offsets of batches 0 and 1, the tile of batch 0, (work lists) record indices of batches 0..2
+    u32 rq = 0;                                                    // work lists: record index two batches ahead
+    {
+        const u32 i0 = gw * 32u + lane, i1 = i0 + bstride, i2 = i1 + bstride;
+        u32 r0 = i0, r1 = i1;
+        if (use_list) {
+            r0 = i0 < count ? a.list[i0] : 0u; r1 = i1 < count ? a.list[i1] : 0u; rq = i2 < count ? a.list[i2] : 0u;
+            sts32(recs, r0); sts32(recs + 128, r1);
+        }
+        if (i0 < count) fetch_offsets(r0, 0);
+        if (i1 < count) fetch_offsets(r1, 1);
+        cp_async_wait_all();
+        __syncwarp();
+        if (gw * 32u < count) {
+            const uint4 oe = lds128(offs);
+            const u64 off = ((u64)oe.y << 32) | oe.x;
+            const u32 n = i0 < count ? oe.z - oe.x : 0u;
+            fetch_tile(0, r0, off, n, is_fast(i0 < count, n));
+        }
+    }
+    u32 kb = 0;                                                    // batch counter of this warp
+    for (u32 b = gw * 32u; b < count; b += bstride, kb++) {
+        const u32 cur = kb & 1u;
         const u32 idx = b + lane;
         const bool have = idx < count;
-        u32 rec = 0, n = 0; u64 off = 0;
-        if (have) {
-            rec = use_list ? a.list[idx] : idx;
-            off = a.offsets[rec];
-            n = (u32)(a.offsets[rec + 1] - off);
+        cp_async_wait_all();
+        __syncwarp();                                              // tile[cur] and the offsets of batch kb + 1 have landed
+        u32 rec = idx; u64 off = 0; u32 n = 0;
+        {
+            const uint4 oe = lds128(offs + 512u * cur);
+            if (use_list) rec = lds32(recs + 128u * (kb % 3u));
+            if (have) { off = ((u64)oe.y << 32) | oe.x; n = oe.z - oe.x; } else rec = 0;
         }
+        {   // next batch -> the other tile; offsets of the batch after it -> the slot just read
+            const u32 idx1 = idx + bstride, idx2 = idx1 + bstride;
+            if (b + bstride < count) {
+                const uint4 oe = lds128(offs + 512u * (cur ^ 1u));
+                u32 rec1 = idx1;
+                if (use_list) rec1 = lds32(recs + 128u * ((kb + 1u) % 3u));
+                const bool have1 = idx1 < count;
+                const u32 n1 = have1 ? oe.z - oe.x : 0u;
+                fetch_tile(cur ^ 1u, have1 ? rec1 : 0u, have1 ? (((u64)oe.y << 32) | oe.x) : 0ull, n1, is_fast(have1, n1));
+            }
+            if (idx2 < count) fetch_offsets(use_list ? rq : idx2, cur);
+            if (use_list) {
+                sts32(recs + 128u * ((kb + 2u) % 3u), rq);
+                const u32 idx3 = idx2 + bstride;
+                rq = idx3 < count ? a.list[idx3] : 0u;
+            }
+        }
+        const u32 tb = wsm + cur * TB + 4u * ROWU * lane;          // this lane's row
+        u32 *Xf = smem + (size_t)wid * (WB / 4) + cur * (TB / 4), *Xr = Xf + a.smem_units;   // generic path: linear strands over the tile
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         // lane-private fast path: 128 <= n <= NMAX (and the long XXH3 form when a hash is wanted)
-        bool fast = in_class && n >= (want_hash ? 241u : 128u) && n <= NMAX;
-        const u64 *src = a.packed2 + ((off >> 5) + rec);
+        bool fast = is_fast(have, n);
         u8 *dst = want_out ? a.out + 16ull * ((off >> 4) + rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
         u64 h = 0;
         const u32 nn = fast ? n : 128u;                            // lanes without a fast record walk a dummy geometry
 
-        // ---- stage: descriptors, then the warp copies record after record into the rows
-        {
-            const u64 sp = reinterpret_cast<u64>(src);
-            sts128(aux + 16u * lane, make_uint4((u32)sp, (u32)(sp >> 32), fast ? (n + 31) >> 5 : 0u, 0u));
-            __syncwarp();
-            if (ROWU <= 36) {                                      // <= 16 words per record: two records per pass
-                const u32 hlf = lane >> 4, k = lane & 15u;
-#pragma unroll 4
-                for (u32 i = 0; i < 16; i++) {
-                    const u32 r = 2 * i + hlf;
-                    const uint4 d = lds128(aux + 16u * r);
-                    if (k < d.z) {
-                        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(((u64)d.y << 32) | d.x) + k);
-                        sts64(wsm + 4u * ROWU * r + 8u * k, w);
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (u32 r = 0; r < 32; r++) {
-                    const uint4 d = lds128(aux + 16u * r);
-                    const uint2 *p = reinterpret_cast<const uint2 *>(((u64)d.y << 32) | d.x);
-#pragma unroll 1
-                    for (u32 k = lane; k < d.z; k += 32) sts64(wsm + 4u * ROWU * r + 8u * k, __ldg(p + k));
-                }
-            }
-            __syncwarp();
-        }
         // ---- circular extension of this lane's row: units jn .. jn + 2 (real bases)
         const u32 jn = nn >> 4, rem = nn & 15u;
         {

@@ -176,11 +176,11 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
-    const u32 t2s = 8u * t2_warp_bytes<36>();
-    if ((rc = set_smem(ctx, k_canon_t2<36, 0>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 1>, t2s)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 2>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 3>, t2s)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 4>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 5>, t2s)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 6>, t2s)) || (rc = set_smem(ctx, k_canon_t2<36, 7>, t2s))) return rc;
+    const u32 t2d = t2_warps<36>(false) * t2_warp_bytes<36>(false), t2l = t2_warps<36>(true) * t2_warp_bytes<36>(true);
+    if ((rc = set_smem(ctx, k_canon_t2<36, 0>, t2d)) || (rc = set_smem(ctx, k_canon_t2<36, 1>, t2d)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 2>, t2d)) || (rc = set_smem(ctx, k_canon_t2<36, 3>, t2d)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 4>, t2l)) || (rc = set_smem(ctx, k_canon_t2<36, 5>, t2l)) ||
+        (rc = set_smem(ctx, k_canon_t2<36, 6>, t2l)) || (rc = set_smem(ctx, k_canon_t2<36, 7>, t2l))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -246,9 +246,10 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             case 6: CK_W2(SM, 6); break; case 7: CK_W2(SM, 7); break; default: CK_W2(SM, -1);                   \
             }
             if (c == CLS_W2S && v >= 0) {
-                // lane-per-record kernel: 3 CTAs of 8 warps per SM, one tile of 32 rows per warp
-                const u32 g2 = 3u * (u32)ctx->num_sms, sm2 = 8u * t2_warp_bytes<36>();
-#define CK_T2(V) k_canon_t2<36, V><<<g2, 256, sm2, st>>>(a)
+                // lane-per-record kernel: 3 CTAs per SM, two tiles of 32 rows per warp
+                const bool ls = a.list != nullptr;
+                const u32 g2 = 3u * (u32)ctx->num_sms, th2 = 32u * t2_warps<36>(ls), sm2 = t2_warps<36>(ls) * t2_warp_bytes<36>(ls);
+#define CK_T2(V) k_canon_t2<36, V><<<g2, th2, sm2, st>>>(a)
                 switch (v) {
                 case 0: CK_T2(0); break; case 1: CK_T2(1); break; case 2: CK_T2(2); break; case 3: CK_T2(3); break;
                 case 4: CK_T2(4); break; case 5: CK_T2(5); break; case 6: CK_T2(6); break; default: CK_T2(7);
