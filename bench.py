@@ -28,13 +28,13 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (records per GPU, length law, lo, hi, dup permille, adversarial permille, uniq?, class mask)
-    "c1": dict(records=1_000_000, kind=0, lo=250, hi=400, dup=0, adv=0, uniq=False, mask=1,
+    "c1": dict(records=1_000_000, kind=0, lo=250, hi=400, dup=0, adv=0, uniq=False,
                desc="config 1: canonicalize, 1M viroid-length (250-400 nt) records"),
-    "c2": dict(records=10_000_000, kind=1, lo=200, hi=5000, dup=300, adv=0, uniq=True, mask=1 | 2,
+    "c2": dict(records=10_000_000, kind=1, lo=200, hi=5000, dup=300, adv=0, uniq=True,
                desc="config 2: uniq, 10M circRNA-length (0.2-5 kb log-uniform) records, 30% rotated/revcomp duplicates"),
-    "c4": dict(records=200_000, kind=1, lo=5000, hi=200_000, dup=0, adv=10, uniq=False, mask=2 | 4 | 8,
+    "c4": dict(records=200_000, kind=1, lo=5000, hi=200_000, dup=0, adv=10, uniq=False,
                desc="config 4: canonicalize, 200k plasmid/mtDNA-length (5-200 kb) records, 1% adversarial repeats"),
-    "c5": dict(records=12_500_000, kind=0, lo=250, hi=400, dup=300, adv=0, uniq=True, mask=1,
+    "c5": dict(records=12_500_000, kind=0, lo=250, hi=400, dup=300, adv=0, uniq=True,
                desc="config 5: uniq, 100M viroid-length records over 8 GPUs (12.5M per GPU), 30% duplicates"),
 }
 SEEDS = {"c1": 1, "c2": 2, "c4": 4, "c5": 5}
@@ -198,6 +198,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     R = w["records"]
+    w["mask"] = D.class_mask_for(w["lo"], w["hi"])
     ctx = circkit_b200.Context(device=local_rank, max_batch_bytes=(256 << 20) if not args.no_e2e else 0,
                                max_batch_records=(1 << 20) if not args.no_e2e else 0,
                                table_capacity=R if (w["uniq"] and not args.no_e2e) else 0)
@@ -274,11 +275,7 @@ def main():
     # ---------------- roofline of the dominant kernel (rank 0's launches)
     from circkit_b200.device import CLASS_NAMES
     dom = max((c for c in CLASS_NAMES if ktimes[c][1]), key=lambda c: ktimes[c][0])
-    bounds = {"2bit_le_512": (1, 512), "2bit_le_8192": (513, 8192), "2bit_le_65536": (8193, 65536),
-              "2bit_le_425984": (65537, 425984)}
-    lo_n, hi_n = bounds.get(dom, (1, 1 << 40))
-    if dom == "2bit_le_8192" and not ktimes["2bit_le_512"][1]:
-        lo_n = 1                 # both warp-shaped classes ran as one launch of the n <= 8192 kernel
+    lo_n, hi_n = D.CLASS_RANGE.get(dom, (1, 1 << 40))
     # bytes this kernel's launch moves by the algorithm: packed read + ASCII write + 16 (+8 hash write);
     # the table's 32 B/record belong to the table kernels, not to this launch
     sel = lens[(lens >= lo_n) & (lens <= hi_n)]
@@ -298,8 +295,7 @@ def main():
         except Exception:
             traffic = None
     kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
-    roofline = {"bound": "hbm", "kernel": "k_canon_%s<%s> [%s]" % ("cta" if "65536" in dom or "425984" in dom else "warp",
-                                                                  dom.split("_")[0], dom),
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_t2 (lane per record)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,

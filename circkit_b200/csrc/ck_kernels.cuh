@@ -15,7 +15,7 @@ namespace ck {
 // record classes (index into the per-class work lists)
 enum : int {
     CLS_W2S = 0,   // 2-bit, warp, n <= 512
-    CLS_W2M = 1,   // 2-bit, warp, n <= 8192
+    CLS_W2M = 1,   // 2-bit, warp, n <= 2048
     CLS_C2A = 2,   // 2-bit, CTA,  n <= 65536
     CLS_C2B = 3,   // 2-bit, CTA,  n <= 425984
     CLS_W4 = 4,    // 4-bit, warp, n <= 2048
@@ -24,12 +24,22 @@ enum : int {
     CLS_C8 = 7,    // bytes, CTA,  n <= 106496
     CLS_HUGE = 8,  // anything longer: strands staged in global scratch
     CLS_EMPTY = 9, // n == 0
-    CLS_COUNT = 10
+    CLS_W2L = 10,  // 2-bit, warp, n <= 4096
+    CLS_W2X = 11,  // 2-bit, warp, n <= 8192
+    CLS_COUNT = 12
 };
 __host__ __device__ constexpr u32 cls_max_n(int c)
 {
-    return c == CLS_W2S ? 512u : c == CLS_W2M ? 8192u : c == CLS_C2A ? 65536u : c == CLS_C2B ? 425984u
-         : c == CLS_W4 ? 2048u : c == CLS_C4 ? 212992u : c == CLS_W8 ? 1024u : c == CLS_C8 ? 106496u : 0xffffffffu;
+    return c == CLS_W2S ? 512u : c == CLS_W2M ? 2048u : c == CLS_W2L ? 4096u : c == CLS_W2X ? 8192u : c == CLS_C2A ? 65536u
+         : c == CLS_C2B ? 425984u : c == CLS_W4 ? 2048u : c == CLS_C4 ? 212992u : c == CLS_W8 ? 1024u : c == CLS_C8 ? 106496u
+         : c == CLS_EMPTY ? 0u : 0xffffffffu;
+}
+// smallest length of a class (the class below it in the same symbol lane ends one short of it)
+__host__ __device__ constexpr u32 cls_min_n(int c)
+{
+    return c == CLS_W2M ? cls_max_n(CLS_W2S) + 1 : c == CLS_W2L ? cls_max_n(CLS_W2M) + 1 : c == CLS_W2X ? cls_max_n(CLS_W2L) + 1
+         : c == CLS_C2A ? cls_max_n(CLS_W2X) + 1 : c == CLS_C2B ? cls_max_n(CLS_C2A) + 1 : c == CLS_C4 ? cls_max_n(CLS_W4) + 1
+         : c == CLS_C8 ? cls_max_n(CLS_W8) + 1 : c == CLS_EMPTY ? 0u : 1u;
 }
 
 struct CanonArgs {
@@ -37,8 +47,8 @@ struct CanonArgs {
     const u8 *bytes;        // normalised byte arena: record i at offsets[i]
     const u64 *offsets;     // n_records + 1 symbol offsets
     const u32 *lens;        // optional normalised lengths (else offsets[i+1] - offsets[i])
-    const u32 *list;        // optional record indices of this class
-    const u32 *count;       // device count of `list` entries (with list), else null
+    const u32 *list;        // optional: the batch's record indices sorted by (class, length); this class's run starts at count[16]
+    const u32 *count;       // device count of this class's entries (with list), else null; count[16] = first entry
     u32 n_direct;           // without list: records [0, n_direct)
     u8 *out;                // canonical ASCII arena (same offsets) or null
     u32 *out_start;         // or null
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(256) k_canon_warp(CanonArgs a)
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
     const u32 count = a.list ? *a.count : a.n_direct;
+    if (a.list) a.list += a.count[16];
     for (u32 e = gw; e < count; e += nw) {
         const u32 rec = a.list ? a.list[e] : e;
         do_record<BITS, G>(a, rec, Xf, Xr, scr, nullptr, nullptr);
@@ -151,6 +162,7 @@ __global__ void __launch_bounds__(1024) k_canon_cta(CanonArgs a)
     u32 *Xr = Xf + a.smem_units;
     u32 *scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
     const u32 count = a.list ? *a.count : a.n_direct;
+    if (a.list) a.list += a.count[16];
     for (u32 e = blockIdx.x; e < count; e += gridDim.x) {
         const u32 rec = a.list ? a.list[e] : e;
         do_record<BITS, G>(a, rec, Xf, Xr, scr, hbuf, red);
@@ -161,6 +173,7 @@ __global__ void __launch_bounds__(1024) k_canon_cta(CanonArgs a)
 __global__ void k_canon_empty(CanonArgs a)
 {
     const u32 count = a.list ? *a.count : a.n_direct;
+    if (a.list) a.list += a.count[16];
     for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const u32 rec = a.list ? a.list[e] : e;
         if (a.list == nullptr && a.offsets[rec + 1] != a.offsets[rec]) continue;
@@ -246,25 +259,29 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_classify: append every record to the work list of its class (order inside a list is irrelevant:
-// each record writes only its own output slots).
+// k_classify: class of every record.  With a class promise (direct_mask) records outside it are counted as
+// "left unprocessed"; otherwise every record gets a sort key (class << 8 | length bin) and the classes are counted:
+// a radix sort of (key, index) then yields ONE index list in which each class is a contiguous run ordered by length,
+// so the lanes of a lane-per-record warp walk records of (nearly) equal length.
 struct ClassifyArgs {
     const u64 *offsets; const u32 *lens; const u8 *lane;   // lane == null: every record is 2-bit
     u32 n_records;
-    u32 *lists;        // CLS_COUNT lists of n_records entries each
-    u32 *counts;       // CLS_COUNT counters (zeroed by the caller)
-    u32 direct_mask;   // != 0: no lists are written (the classes of the mask run over all records directly);
+    u32 *keys, *vals;  // n_records sort keys / record indices (list mode)
+    u32 *counts;       // 16 class counters (zeroed by the caller), followed by 16 run starts (k_list_starts)
+    u32 direct_mask;   // != 0: no keys are written (the classes of the mask run over all records directly);
                        // records of any other class are counted in counts[CLS_HUGE] = "left unprocessed"
 };
 __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     int cls = -1;
+    u32 n = 0;
     if (i < a.n_records) {
-        const u32 n = a.lens ? a.lens[i] : (u32)(a.offsets[i + 1] - a.offsets[i]);
+        n = a.lens ? a.lens[i] : (u32)(a.offsets[i + 1] - a.offsets[i]);
         const u32 bits = a.lane ? a.lane[i] : 2u;
         if (n == 0) cls = CLS_EMPTY;
         else if (bits == 2) cls = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M
+                                : n <= cls_max_n(CLS_W2L) ? CLS_W2L : n <= cls_max_n(CLS_W2X) ? CLS_W2X
                                 : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
         else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
         else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
@@ -274,15 +291,19 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
         if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + CLS_HUGE, __popc(m));
         return;
     }
-    // warp-aggregated append, one atomic per (warp, class present)
+    if (cls >= 0) { a.keys[i] = ((u32)cls << 8) | min((n + 31u) >> 5, 255u); a.vals[i] = i; }
+    // warp-aggregated counting, one atomic per (warp, class present)
     for (int c = 0; c < CLS_COUNT; c++) {
         const u32 m = __ballot_sync(CK_FULL, cls == c);
-        if (!m) continue;
-        u32 base = 0;
-        const u32 leader = __ffs(m) - 1;
-        if (lane_id() == leader) base = atomicAdd(a.counts + c, __popc(m));
-        base = __shfl_sync(CK_FULL, base, leader);
-        if (cls == c) a.lists[(size_t)c * a.n_records + base + __popc(m & ((1u << lane_id()) - 1u))] = i;
+        if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + c, __popc(m));
+    }
+}
+// run starts of the sorted index list: starts[c] = number of records in classes below c
+__global__ void k_list_starts(u32 *counts)
+{
+    if (threadIdx.x == 0) {
+        u32 s = 0;
+        for (int c = 0; c < 16; c++) { counts[16 + c] = s; s += c < CLS_COUNT ? counts[c] : 0u; }
     }
 }
 

@@ -49,13 +49,18 @@ __device__ __forceinline__ void sts128(u32 a, uint4 v)
 // two batches in flight, and (work-list launches) the record indices of three batches
 #define CK_T2_AUX_BYTES 2560u
 template <int ROWU> __host__ __device__ constexpr u32 t2_tile_bytes() { return 32u * ROWU * 4u; }
+template <int ROWU> __host__ __device__ constexpr u32 t2_tiles() { return ROWU <= 36 ? 2u : 1u; }   // long rows: one tile, batch latency is amortised
 template <int ROWU> __host__ __device__ constexpr u32 t2_warp_bytes(bool list)
 {
-    return 2u * t2_tile_bytes<ROWU>() + CK_T2_AUX_BYTES + 1024u + (list ? 384u : 0u);
+    return t2_tiles<ROWU>() * t2_tile_bytes<ROWU>() + CK_T2_AUX_BYTES + 1024u + (list ? 384u : 0u);
 }
 template <int ROWU> __host__ __device__ constexpr u32 t2_max_n() { return 16u * (ROWU - 4); }
-// warps per CTA: as many as three (short rows) CTAs per SM can hold in 227 KB
-template <int ROWU> __host__ __device__ constexpr u32 t2_warps(bool list) { return ROWU <= 36 ? (list ? 5u : 6u) : 1u; }
+// warps per CTA and CTAs per SM: what 227 KB of shared memory hold
+template <int ROWU> __host__ __device__ constexpr u32 t2_warps(bool list)
+{
+    return ROWU <= 36 ? (list ? 5u : 6u) : ROWU <= 132 ? 5u : ROWU <= 260 ? 3u : 1u;
+}
+template <int ROWU> __host__ __device__ constexpr u32 t2_ctas() { return ROWU <= 36 ? 3u : ROWU <= 260 ? 2u : 3u; }
 
 __device__ __forceinline__ void cp_async8(u32 dst, const void *src)
 {
@@ -101,20 +106,22 @@ __device__ __forceinline__ void t2_acc16(u64 &a0, u64 &a1, uint4 v, u64 k0, u64 
 }
 
 template <int ROWU, int V>
-__global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), (ROWU <= 36 ? 3 : 1)) k_canon_t2(CanonArgs a)
+__global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), t2_ctas<ROWU>()) k_canon_t2(CanonArgs a)
 {
     extern __shared__ __align__(16) u32 smem[];
     constexpr bool want_hash = (V & CK_W2_HASH) != 0, want_out = (V & CK_W2_OUT) != 0, use_list = (V & CK_W2_LIST) != 0;
     constexpr u32 TB = t2_tile_bytes<ROWU>(), WB = t2_warp_bytes<ROWU>(use_list), NMAX = t2_max_n<ROWU>();
     constexpr bool BLOCKS = NMAX > 1024;                           // XXH3 block scrambles can occur
+    constexpr bool DB = t2_tiles<ROWU>() == 2;                     // double-buffered tiles
     const u32 lane = lane_id(), wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 wsm = (u32)__cvta_generic_to_shared(smem) + wid * WB;  // this warp's tiles
-    const u32 aux = wsm + 2u * TB;                                 // descriptors / output stage
+    const u32 aux = wsm + t2_tiles<ROWU>() * TB;                   // descriptors / output stage
     const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
     const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
     const u32 count = use_list ? *a.count : a.n_direct;
+    if (use_list) a.list += a.count[16];
     const u32 bstride = nw * 32u;
 
     // request the (offset, end) pair of record `rec` into slot `slot`
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), (R
         if (i1 < count) fetch_offsets(r1, 1);
         cp_async_wait_all();
         __syncwarp();
-        if (gw * 32u < count) {
+        if (DB && gw * 32u < count) {
             const uint4 oe = lds128(offs);
             const u64 off = ((u64)oe.y << 32) | oe.x;
             const u32 n = i0 < count ? oe.z - oe.x : 0u;
@@ -174,33 +181,35 @@ __global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), (R
     }
     u32 kb = 0;                                                    // batch counter of this warp
     for (u32 b = gw * 32u; b < count; b += bstride, kb++) {
-        const u32 cur = kb & 1u;
+        const u32 sl = kb & 1u, cur = DB ? sl : 0u;                // offsets slot / tile of this batch
         const u32 idx = b + lane;
         const bool have = idx < count;
         cp_async_wait_all();
-        __syncwarp();                                              // tile[cur] and the offsets of batch kb + 1 have landed
+        __syncwarp();                                              // the offsets of batches kb, kb + 1 (and tile[cur]) have landed
         u32 rec = idx; u64 off = 0; u32 n = 0;
         {
-            const uint4 oe = lds128(offs + 512u * cur);
+            const uint4 oe = lds128(offs + 512u * sl);
             if (use_list) rec = lds32(recs + 128u * (kb % 3u));
             if (have) { off = ((u64)oe.y << 32) | oe.x; n = oe.z - oe.x; } else rec = 0;
         }
-        {   // next batch -> the other tile; offsets of the batch after it -> the slot just read
+        {   // next batch -> the other tile (or this batch -> the only tile); offsets of the batch after the next -> the slot just read
             const u32 idx1 = idx + bstride, idx2 = idx1 + bstride;
-            if (b + bstride < count) {
-                const uint4 oe = lds128(offs + 512u * (cur ^ 1u));
+            if (!DB) fetch_tile(0, rec, off, n, is_fast(have, n));
+            else if (b + bstride < count) {
+                const uint4 oe = lds128(offs + 512u * (sl ^ 1u));
                 u32 rec1 = idx1;
                 if (use_list) rec1 = lds32(recs + 128u * ((kb + 1u) % 3u));
                 const bool have1 = idx1 < count;
                 const u32 n1 = have1 ? oe.z - oe.x : 0u;
                 fetch_tile(cur ^ 1u, have1 ? rec1 : 0u, have1 ? (((u64)oe.y << 32) | oe.x) : 0ull, n1, is_fast(have1, n1));
             }
-            if (idx2 < count) fetch_offsets(use_list ? rq : idx2, cur);
+            if (idx2 < count) fetch_offsets(use_list ? rq : idx2, sl);
             if (use_list) {
                 sts32(recs + 128u * ((kb + 2u) % 3u), rq);
                 const u32 idx3 = idx2 + bstride;
                 rq = idx3 < count ? a.list[idx3] : 0u;
             }
+            if (!DB) { cp_async_wait_all(); __syncwarp(); }
         }
         const u32 tb = wsm + cur * TB + 4u * ROWU * lane;          // this lane's row
         u32 *Xf = smem + (size_t)wid * (WB / 4) + cur * (TB / 4), *Xr = Xf + a.smem_units;   // generic path: linear strands over the tile

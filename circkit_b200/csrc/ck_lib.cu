@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/circkit_b200.h"
@@ -35,6 +36,8 @@ const ClsCfg kCls[CLS_COUNT] = {
     {8, true, 1024, 1},   // CLS_C8
     {0, true, 0, 0},      // CLS_HUGE (handled separately)
     {0, false, 256, 1},   // CLS_EMPTY
+    {2, false, 256, 6},   // CLS_W2L
+    {2, false, 256, 6},   // CLS_W2X
 };
 
 u32 cls_units(int c)
@@ -58,7 +61,7 @@ u64 cls_tie_words(int c)
 u32 cls_smem_bytes(int c)
 {
     const u32 per = 2u * cls_units(c) * 4u;
-    if (c == CLS_W2S || c == CLS_W2M) return (u32)sizeof(W2Const) + per * (kCls[c].threads / 32u);
+    if (c == CLS_W2S || c == CLS_W2M || c == CLS_W2L || c == CLS_W2X) return (u32)sizeof(W2Const) + per * (kCls[c].threads / 32u);
     return kCls[c].cta ? per : per * (kCls[c].threads / 32u);
 }
 
@@ -169,6 +172,29 @@ template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
     if (bytes > 48 * 1024) CK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return CK_OK;
 }
+// lane-per-record kernel (ck_lane2.cuh): shared-memory opt-in and launch of variant v (CK_W2_* bits) for one row size
+template <int ROWU> int t2_attrs(ck_ctx *ctx)
+{
+    const u32 d = t2_warps<ROWU>(false) * t2_warp_bytes<ROWU>(false), l = t2_warps<ROWU>(true) * t2_warp_bytes<ROWU>(true);
+    int rc;
+    if ((rc = set_smem(ctx, k_canon_t2<ROWU, 0>, d)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 1>, d)) ||
+        (rc = set_smem(ctx, k_canon_t2<ROWU, 2>, d)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 3>, d)) ||
+        (rc = set_smem(ctx, k_canon_t2<ROWU, 4>, l)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 5>, l)) ||
+        (rc = set_smem(ctx, k_canon_t2<ROWU, 6>, l)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 7>, l))) return rc;
+    return CK_OK;
+}
+template <int ROWU> void t2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
+{
+    const bool ls = a.list != nullptr;
+    const u32 g = t2_ctas<ROWU>() * (u32)ctx->num_sms, th = 32u * t2_warps<ROWU>(ls), sm = t2_warps<ROWU>(ls) * t2_warp_bytes<ROWU>(ls);
+#define CK_T2(V) k_canon_t2<ROWU, V><<<g, th, sm, st>>>(a)
+    switch (v) {
+    case 0: CK_T2(0); break; case 1: CK_T2(1); break; case 2: CK_T2(2); break; case 3: CK_T2(3); break;
+    case 4: CK_T2(4); break; case 5: CK_T2(5); break; case 6: CK_T2(6); break; default: CK_T2(7);
+    }
+#undef CK_T2
+}
+
 int set_attrs(ck_ctx *ctx)
 {
     if (ctx->attrs_set) return CK_OK;
@@ -176,11 +202,7 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
-    const u32 t2d = t2_warps<36>(false) * t2_warp_bytes<36>(false), t2l = t2_warps<36>(true) * t2_warp_bytes<36>(true);
-    if ((rc = set_smem(ctx, k_canon_t2<36, 0>, t2d)) || (rc = set_smem(ctx, k_canon_t2<36, 1>, t2d)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 2>, t2d)) || (rc = set_smem(ctx, k_canon_t2<36, 3>, t2d)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 4>, t2l)) || (rc = set_smem(ctx, k_canon_t2<36, 5>, t2l)) ||
-        (rc = set_smem(ctx, k_canon_t2<36, 6>, t2l)) || (rc = set_smem(ctx, k_canon_t2<36, 7>, t2l))) return rc;
+    if ((rc = t2_attrs<36>(ctx)) || (rc = t2_attrs<132>(ctx)) || (rc = t2_attrs<260>(ctx)) || (rc = t2_attrs<516>(ctx))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -189,8 +211,12 @@ struct CanonIO {
     const u64 *packed2; const u8 *bytes; const u64 *offsets; const u32 *lens; const u8 *lane;
     u32 n; u32 mode;
     u8 *out; u32 *out_start; u8 *out_strand; u64 *out_hash;
-    u32 *lists; u32 *counts;          // CLS_COUNT * n and 16 u32
+    u32 *lists; u64 lists_bytes;      // sort workspace: >= ck_lists_bytes(n)
+    u32 *counts;                      // 32 u32: class counts, run starts
 };
+
+// sort workspace of a batch of n records: two (key, index) buffer pairs + radix-sort temporaries
+u64 lists_bytes_for(u64 n) { return 16 * (n + 4) + 24 * (n + 4) + (1ull << 20); }
 
 // classify + one launch per class.  counts[CLS_HUGE] > 0 afterwards means unprocessed records.
 int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io, u32 class_mask)
@@ -198,31 +224,39 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     if (io.n == 0) return CK_OK;
     int rc = set_attrs(ctx);
     if (rc) return rc;
-    CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 16 * sizeof(u32), st));
-    // a promise of exactly one class lets that class index the records directly (no work lists); the two warp-shaped
-    // 2-bit classes together run as ONE direct launch of the n <= 8192 kernel
+    CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 32 * sizeof(u32), st));
+    // a promise of exactly one class lets that class index the records directly (no work lists)
     int only = -1;
-    const bool merged = false;     // every class runs its own kernel (the n <= 512 class has the lane-per-record kernel)
     if (class_mask && (class_mask & (class_mask - 1)) == 0)
         for (int c = 0; c < CLS_COUNT; c++) if (class_mask == (1u << c)) only = c;
-    if (merged) only = CLS_W2M;
-    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, io.lists, io.counts, only >= 0 ? (merged ? class_mask : (1u << only)) : 0u};
+    const u64 stride = ((u64)io.n + 4) & ~3ull;                // u32 elements per sort buffer
+    u32 *k0 = io.lists, *k1 = k0 + stride, *v0 = k1 + stride, *v1 = v0 + stride;
+    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u};
     k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
     ctx->launches++;
+    const u32 *sorted = nullptr;
+    if (only < 0) {
+        // one index list for the whole batch: classes are contiguous runs, each ordered by length
+        if (io.lists_bytes < 16 * stride) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
+        cub::DoubleBuffer<u32> keys(k0, k1), vals(v0, v1);
+        void *tmp = v1 + stride;
+        size_t tmp_bytes = (size_t)(io.lists_bytes - 16 * stride), need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)io.n, 0, 12, st);
+        if (need > tmp_bytes) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
+        CK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, (int)io.n, 0, 12, st));
+        sorted = vals.Current();
+        k_list_starts<<<1, 32, 0, st>>>(io.counts);
+        ctx->launches += 2;
+    }
     for (int c = 0; c < CLS_COUNT; c++) {
         if (c == CLS_HUGE) continue;
         if (class_mask && !(class_mask & (1u << c))) continue;
-        if (merged && c == CLS_W2S) continue;
         CanonArgs a{};
         a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
         if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
-        else { a.list = io.lists + (size_t)c * io.n; a.count = io.counts + c; a.n_direct = 0; }
+        else { a.list = sorted; a.count = io.counts + c; a.n_direct = 0; }
         a.max_n = cls_max_n(c);
-        a.min_n = (c == CLS_W2M) ? cls_max_n(CLS_W2S) + 1 : (c == CLS_C2A) ? cls_max_n(CLS_W2M) + 1
-                : (c == CLS_C2B) ? cls_max_n(CLS_C2A) + 1 : (c == CLS_C4) ? cls_max_n(CLS_W4) + 1
-                : (c == CLS_C8) ? cls_max_n(CLS_W8) + 1 : (c == CLS_EMPTY ? 0u : 1u);
-        if (c == CLS_EMPTY) a.max_n = 0;
-        if (merged) a.min_n = 1;
+        a.min_n = cls_min_n(c);
         a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
         a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
         a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
@@ -234,30 +268,18 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
             CK_CUDA(ctx, cudaEventRecord(e0, st));
         }
         switch (c) {
-        case CLS_W2S: case CLS_W2M: {
-            // specialised variants for the resident fast path (direct range, both strands, aligned bytes or none)
+        case CLS_W2S: case CLS_W2M: case CLS_W2L: case CLS_W2X: {
+            // specialised variants for the resident fast path (packed lengths, both strands, aligned bytes or none):
+            // the lane-per-record kernel; everything else: the run-time-option warp-per-record kernel
             const bool fast = !a.lens && !(a.mode & 1u) && (!a.out || (a.mode & 2u)) && a.out_start && a.out_strand;
             const int v = fast ? ((a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0)) : -1;
-#define CK_W2(SM, V) k_canon_w2<SM, V><<<grid, thr, smem, st>>>(a)
-#define CK_W2_SWITCH(SM)                                                                                        \
-            switch (v) {                                                                                        \
-            case 0: CK_W2(SM, 0); break; case 1: CK_W2(SM, 1); break; case 2: CK_W2(SM, 2); break;              \
-            case 3: CK_W2(SM, 3); break; case 4: CK_W2(SM, 4); break; case 5: CK_W2(SM, 5); break;              \
-            case 6: CK_W2(SM, 6); break; case 7: CK_W2(SM, 7); break; default: CK_W2(SM, -1);                   \
-            }
-            if (c == CLS_W2S && v >= 0) {
-                // lane-per-record kernel: 3 CTAs per SM, two tiles of 32 rows per warp
-                const bool ls = a.list != nullptr;
-                const u32 g2 = 3u * (u32)ctx->num_sms, th2 = 32u * t2_warps<36>(ls), sm2 = t2_warps<36>(ls) * t2_warp_bytes<36>(ls);
-#define CK_T2(V) k_canon_t2<36, V><<<g2, th2, sm2, st>>>(a)
-                switch (v) {
-                case 0: CK_T2(0); break; case 1: CK_T2(1); break; case 2: CK_T2(2); break; case 3: CK_T2(3); break;
-                case 4: CK_T2(4); break; case 5: CK_T2(5); break; case 6: CK_T2(6); break; default: CK_T2(7);
-                }
-#undef CK_T2
-            } else if (c == CLS_W2S) { CK_W2_SWITCH(true) } else { CK_W2_SWITCH(false) }
-#undef CK_W2_SWITCH
-#undef CK_W2
+            if (v >= 0) {
+                if (c == CLS_W2S) t2_launch<36>(ctx, st, a, v);
+                else if (c == CLS_W2M) t2_launch<132>(ctx, st, a, v);
+                else if (c == CLS_W2L) t2_launch<260>(ctx, st, a, v);
+                else t2_launch<516>(ctx, st, a, v);
+            } else if (c == CLS_W2S) k_canon_w2<true, -1><<<grid, thr, smem, st>>>(a);
+            else k_canon_w2<false, -1><<<grid, thr, smem, st>>>(a);
             break;
         }
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
@@ -332,7 +354,7 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
-    io.lists = s.d_lists; io.counts = s.d_counts;
+    io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
     int rc = run_canon(ctx, st, s.scr, io, 0);
     if (rc) return rc;
     if (uniq) {
@@ -428,8 +450,8 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaMalloc(&s.d_hash, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_first, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_slotof, (R + 1) * 8));
-            CK_INIT(cudaMalloc(&s.d_lists, (size_t)CLS_COUNT * (R + 1) * 4));
-            CK_INIT(cudaMalloc(&s.d_counts, 16 * 4));
+            CK_INIT(cudaMalloc(&s.d_lists, lists_bytes_for(R)));
+            CK_INIT(cudaMalloc(&s.d_counts, 32 * 4));
             CK_INIT(cudaMallocHost(&s.h_counts, 32 * 4));
             memset(s.h_counts, 0, 32 * 4);
             if (alloc_scratch(ctx, s.scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
@@ -533,7 +555,7 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     CK_LB(cudaMalloc(&d_raw, total + 16)); CK_LB(cudaMalloc(&d_norm, total + 16)); CK_LB(cudaMalloc(&d_out, total + 16));
     CK_LB(cudaMalloc(&d_p2, (total / 32 + R + 2) * 8)); CK_LB(cudaMalloc(&d_off, (R + 1) * 8));
     CK_LB(cudaMalloc(&d_len, R * 4)); CK_LB(cudaMalloc(&d_lane, R)); CK_LB(cudaMalloc(&d_start, R * 4));
-    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, (size_t)CLS_COUNT * R * 4)); CK_LB(cudaMalloc(&d_counts, 64));
+    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, lists_bytes_for(R))); CK_LB(cudaMalloc(&d_counts, 128));
     CK_LB(cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice));
     if (total) CK_LB(cudaMemcpy(d_raw, bytes, total, cudaMemcpyHostToDevice));
     if (e == cudaSuccess) {
@@ -543,7 +565,7 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
         CanonIO io{};
         io.packed2 = d_p2; io.bytes = d_norm; io.offsets = d_off; io.lens = d_len; io.lane = d_lane; io.n = n_records;
         io.mode = mode; io.out = out_bytes ? d_out : nullptr; io.out_start = d_start; io.out_strand = d_strand;
-        io.out_hash = nullptr; io.lists = d_lists; io.counts = d_counts;
+        io.out_hash = nullptr; io.lists = d_lists; io.lists_bytes = lists_bytes_for(R); io.counts = d_counts;
         rc = run_canon(ctx, 0, ctx->dev_scr, io, 0);
     }
     if (rc == CK_OK) {
@@ -591,7 +613,7 @@ int ck_canonicalize(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out)
 // ---- device-resident API ---------------------------------------------------------------------
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
 {
-    u64 b = 256 + (u64)CLS_COUNT * 4 * ((u64)n_records + 1);
+    u64 b = 256 + lists_bytes_for(n_records);
     if (total_bytes) b += (total_bytes / 32 + n_records + 2) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
     return (b + 255) & ~255ull;
 }
@@ -607,7 +629,7 @@ int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, con
     io.packed2 = U(packed2); io.offsets = U(offsets); io.n = n_records;
     io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand; io.out_hash = U(out_hash64);
-    io.counts = (u32 *)workspace; io.lists = (u32 *)((u8 *)workspace + 256);
+    io.counts = (u32 *)workspace; io.lists = (u32 *)((u8 *)workspace + 256); io.lists_bytes = lists_bytes_for(n_records);
     return run_canon(ctx, (cudaStream_t)stream, ctx->dev_scr, io, class_mask);
 }
 int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
@@ -622,7 +644,7 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     if (!n_records) return CK_OK;
     u8 *w = (u8 *)workspace;
     u32 *counts = (u32 *)w; w += 256;
-    u32 *lists = (u32 *)w; w += (u64)CLS_COUNT * 4 * ((u64)n_records + 1);
+    u32 *lists = (u32 *)w; w += lists_bytes_for(n_records);
     u64 *p2 = (u64 *)w; w += (total_bytes / 32 + n_records + 2) * 8;
     u8 *norm = w; w += (total_bytes + 63) & ~63ull;
     u8 *lane = w;
@@ -634,7 +656,7 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
     io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand;
-    io.out_hash = U(out_hash64); io.counts = counts; io.lists = lists;
+    io.out_hash = U(out_hash64); io.counts = counts; io.lists = lists; io.lists_bytes = lists_bytes_for(n_records);
     return run_canon(ctx, st, ctx->dev_scr, io, class_mask);
 }
 int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace)

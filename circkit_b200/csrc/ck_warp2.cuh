@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
     u32 *scr = a.scratch + (size_t)gw * a.scratch_stride;
     const bool use_list = RT ? a.list != nullptr : (V & CK_W2_LIST) != 0;
     const u32 count = use_list ? *a.count : a.n_direct;
+    if (use_list) a.list += a.count[16];
     const bool fwd_only = RT && (a.mode & 1u) != 0;
     const bool aligned_out = RT ? (a.mode & 2u) != 0 : true;
     const bool want_hash = RT ? a.out_hash != nullptr : (V & CK_W2_HASH) != 0;

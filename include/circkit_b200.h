@@ -104,9 +104,11 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
  * length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
  * records outside the promise are reported by ck_dev_check(), never silently dropped. */
 #define CK_CLASS_2BIT_LE_512 (1u << 0)
-#define CK_CLASS_2BIT_LE_8192 (1u << 1)
+#define CK_CLASS_2BIT_LE_2048 (1u << 1)
 #define CK_CLASS_2BIT_LE_65536 (1u << 2)
 #define CK_CLASS_2BIT_LE_425984 (1u << 3)
+#define CK_CLASS_2BIT_LE_4096 (1u << 10)
+#define CK_CLASS_2BIT_LE_8192 (1u << 11)
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes /* 0 for the packed2 entry */);
 /* bytes of the CK_F_ALIGNED_OUT arena of a batch (host and device entries) */
 uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records);

@@ -28,9 +28,9 @@ def _oracle_for(ctx, D, torch, batch, n):
 
 @pytest.mark.parametrize("name,kind,lo,hi,dup,adv,mask,n", [
     ("c1-like direct mode", 0, 250, 400, 0, 0, 1, 30000),
-    ("c2-like two classes", 1, 200, 5000, 300, 0, 3, 12000),
+    ("c2-like four classes", 1, 200, 5000, 300, 0, 1 | 2 | 1 << 10 | 1 << 11, 12000),
     ("c5-like dups", 0, 250, 400, 300, 0, 1, 30000),
-    ("c4-like long + adversarial", 1, 5000, 200000, 0, 100, 2 | 4 | 8, 300),
+    ("c4-like long + adversarial", 1, 5000, 200000, 0, 100, 1 << 11 | 4 | 8, 300),
     ("all classes, no promise", 1, 64, 20000, 200, 20, 0, 3000),
     ("short and tiny", 0, 1, 130, 100, 0, 0, 20000),
 ])
