@@ -295,7 +295,7 @@ def main():
         except Exception:
             traffic = None
     kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
-    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_t2 (lane per record)", dom),
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_s2 (lane per record, streaming)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,

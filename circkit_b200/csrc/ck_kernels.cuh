@@ -42,8 +42,20 @@ __host__ __device__ constexpr u32 cls_min_n(int c)
          : c == CLS_C8 ? cls_max_n(CLS_W8) + 1 : c == CLS_EMPTY ? 0u : 1u;
 }
 
+// order of the classes in the sorted index list: the lane-kernel classes first, contiguous, by length
+__host__ __device__ constexpr u32 cls_rank(int c)
+{
+    return c == CLS_W2S ? 0u : c == CLS_W2M ? 1u : c == CLS_W2L ? 2u : c == CLS_W2X ? 3u : c == CLS_C2A ? 4u : c == CLS_C2B ? 5u
+         : c == CLS_W4 ? 6u : c == CLS_C4 ? 7u : c == CLS_W8 ? 8u : c == CLS_C8 ? 9u : c == CLS_HUGE ? 10u : 11u;
+}
+__host__ __device__ constexpr int cls_of_rank(u32 r)
+{
+    return r == 0 ? CLS_W2S : r == 1 ? CLS_W2M : r == 2 ? CLS_W2L : r == 3 ? CLS_W2X : r == 4 ? CLS_C2A : r == 5 ? CLS_C2B
+         : r == 6 ? CLS_W4 : r == 7 ? CLS_C4 : r == 8 ? CLS_W8 : r == 9 ? CLS_C8 : r == 10 ? CLS_HUGE : CLS_EMPTY;
+}
+
 struct CanonArgs {
-    const u64 *packed2;     // 2-bit arena (16-base u32 units, MSB-first): record i at u64 index (offsets[i] >> 5) + i
+    const u64 *packed2;     // 2-bit arena (ck_device.cuh): record i at u64 index p2_word(offsets[i], i)
     const u8 *bytes;        // normalised byte arena: record i at offsets[i]
     const u64 *offsets;     // n_records + 1 symbol offsets
     const u32 *lens;        // optional normalised lengths (else offsets[i+1] - offsets[i])
@@ -61,6 +73,8 @@ struct CanonArgs {
     u32 mode;               // bit0: forward strand only (lmsr / lmsr_index, lib/src/canonicalize.rs:5,41)
                             // bit1: aligned output arena: record i's bytes start at 16 * ((offsets[i] >> 4) + i)
     u32 min_n, max_n;       // length range of this launch's class (checked when there is no list)
+    u32 *retry;             // lane-per-record kernel: records it leaves to the warp / CTA kernels, appended per class at
+    u32 *retry_counts;      // retry[retry_counts[16 + class] + atomicAdd(retry_counts + class, 1)]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -116,7 +130,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
     const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
     if (a.list == nullptr && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform)
     RecordIn in;
-    in.packed2 = a.packed2 ? a.packed2 + ((off >> 5) + rec) : nullptr;
+    in.packed2 = a.packed2 ? a.packed2 + p2_word(off, rec) : nullptr;
     in.bytes = a.bytes ? a.bytes + off : nullptr;
     in.n = n;
     stage_record<BITS, G>(in, Xf, Xr);
@@ -189,7 +203,7 @@ __global__ void k_canon_empty(CanonArgs a)
 //                           (whitespace dropped, acgt -> upper, t/u/U -> T, ./~ -> -, anything else -> N)
 //   otherwise             : library semantics, bytes are taken as they are (lib/src/canonicalize.rs:54)
 // Writes lens[i], lane[i] (2, 4 or 8 bits per symbol) and the record in that lane's format:
-//   lane 2 -> packed2 at word (offsets[i] >> 5) + i;   lanes 4/8 -> normalised bytes at offsets[i].
+//   lane 2 -> packed2 at word p2_word(offsets[i], i);   lanes 4/8 -> normalised bytes at offsets[i].
 struct PrepareArgs {
     const u8 *raw; const u64 *offsets; u32 n_records; u32 flags;
     u64 *packed2; u8 *bytes; u32 *lens; u8 *lane;
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
         const u32 lanebits = cls == 0 ? 2u : (cls == 1 ? 4u : 8u);
         if (lane == 0) { a.lens[rec] = cnt; a.lane[rec] = (u8)lanebits; }
         // pass 2: write in the lane's format
-        u64 *dstw = a.packed2 + ((off >> 5) + rec);
+        u64 *dstw = a.packed2 + p2_word(off, rec);
         u8 *dstb = a.bytes + off;
         u32 done = 0;                 // normalised symbols written so far
         u32 acc_hi = 0, acc_lo = 0;   // word under construction (uniform across the warp)
@@ -291,20 +305,65 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
         if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + CLS_HUGE, __popc(m));
         return;
     }
-    if (cls >= 0) { a.keys[i] = ((u32)cls << 8) | min((n + 31u) >> 5, 255u); a.vals[i] = i; }
+    if (cls >= 0) {
+        // key = (rank of the class in list order) : (length on a 1/32-octave log scale)
+        const u32 msb = 31u - __clz(n | 1u);
+        const u32 bin = (msb << 5) | (((n << (31u - msb)) >> 26) & 31u);
+        a.keys[i] = (cls_rank(cls) << 10) | bin; a.vals[i] = i;
+    }
     // warp-aggregated counting, one atomic per (warp, class present)
     for (int c = 0; c < CLS_COUNT; c++) {
         const u32 m = __ballot_sync(CK_FULL, cls == c);
         if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + c, __popc(m));
     }
 }
-// run starts of the sorted index list: starts[c] = number of records in classes below c
+// run starts of the sorted index list (classes in cls_rank order).  Layout of the 64 counters:
+//   [0, 12)  records per class        [12]  records of the lane-kernel classes together (one launch)
+//   [16, 28) first entry per class    [28]  first entry of the lane-kernel classes
+//   [32, 44) retry entries per class  [48, 60)  first retry entry per class (= first entry of the class)
 __global__ void k_list_starts(u32 *counts)
 {
     if (threadIdx.x == 0) {
         u32 s = 0;
-        for (int c = 0; c < 16; c++) { counts[16 + c] = s; s += c < CLS_COUNT ? counts[c] : 0u; }
+        for (u32 r = 0; r < (u32)CLS_COUNT; r++) {
+            const int c = cls_of_rank(r);
+            counts[16 + c] = s; counts[48 + c] = s;
+            s += counts[c];
+        }
+        counts[12] = counts[CLS_W2S] + counts[CLS_W2M] + counts[CLS_W2L] + counts[CLS_W2X];
+        counts[28] = counts[16 + CLS_W2S];
     }
+}
+
+// k_extend_packed2: append the circular extension to every packed record (units jn .. jn + 3, jn = n >> 4; the
+// partial unit jn keeps its real bases).  One thread per record; runs after the packer (k_prepare / k_synth_packed2).
+__global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane, u32 n_records)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_records) return;
+    if (lane && lane[i] != 2) return;
+    const u64 off = offsets[i];
+    const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
+    if (n == 0) return;
+    u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i));
+    const u32 jn = n >> 4, rem = n & 15u;
+    u32 e[4];
+    if (n >= 64) {
+        const u32 u0 = U[0], u1 = U[1], u2 = U[2], u3 = U[3], uj = U[jn];
+        const u32 sh = 32u - 2u * rem;
+        e[0] = (uj & ~(0xffffffffu >> (2 * rem))) | (u0 >> (2 * rem));
+        e[1] = __funnelshift_lc(u1, u0, sh); e[2] = __funnelshift_lc(u2, u1, sh); e[3] = __funnelshift_lc(u3, u2, sh);
+    } else {
+        for (u32 k = 0; k < 4; k++) {
+            u32 v = 0;
+            for (u32 b = 0; b < 16; b++) {
+                const u32 t = (16 * (jn + k) + b) % n;
+                v = (v << 2) | ((U[t >> 4] >> (30 - 2 * (t & 15))) & 3u);
+            }
+            e[k] = v;
+        }
+    }
+    U[jn] = e[0]; U[jn + 1] = e[1]; U[jn + 2] = e[2]; U[jn + 3] = e[3];
 }
 
 // ---------------------------------------------------------------------------------------------

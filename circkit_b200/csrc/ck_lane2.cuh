@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), t2
     };
     // request the packed words of a batch into tile `tile`: descriptors, then the warp copies record after record
     auto fetch_tile = [&](u32 tile, u32 rec, u64 off, u32 n, bool want) {
-        const u64 sp = reinterpret_cast<u64>(a.packed2 + ((off >> 5) + rec));
+        const u64 sp = reinterpret_cast<u64>(a.packed2 + p2_word(off, rec));
         sts128(aux + 16u * lane, make_uint4((u32)sp, (u32)(sp >> 32), want ? (n + 31) >> 5 : 0u, 0u));
         __syncwarp();
         const u32 tw = wsm + tile * TB;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(32 * t2_warps<ROWU>((V & CK_W2_LIST) != 0), t2
                 const u64 off_l = __shfl_sync(CK_FULL, off, L);
                 u8 *dst_l = want_out ? a.out + 16ull * ((off_l >> 4) + rec_l) : nullptr;
                 __syncwarp();
-                const u32 os_l = w2_tiny_record(a.packed2 + ((off_l >> 5) + rec_l), n_l, dst_l, Xf, Xr, scr, false);
+                const u32 os_l = w2_tiny_record(a.packed2 + p2_word(off_l, rec_l), n_l, dst_l, Xf, Xr, scr, false);
                 u64 h_l = 0;
                 if (want_hash) h_l = w2_any_hash((os_l & 1u) ? Xr : Xf, n_l, os_l >> 1);
                 if (lane == 0) {

@@ -13,6 +13,7 @@
 #include "ck_kernels.cuh"
 #include "ck_warp2.cuh"
 #include "ck_lane2.cuh"
+#include "ck_stream2.cuh"
 #include "ck_synth.cuh"
 
 using namespace ck;
@@ -99,7 +100,7 @@ struct ck_ctx {
     bool attrs_set = false;
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
-    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 2];     // [CLS_COUNT] = table insert, [CLS_COUNT+1] = table first
+    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 3];     // [CLS_COUNT] = lane kernel, then table insert, table first
 };
 
 namespace {
@@ -172,27 +173,16 @@ template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
     if (bytes > 48 * 1024) CK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return CK_OK;
 }
-// lane-per-record kernel (ck_lane2.cuh): shared-memory opt-in and launch of variant v (CK_W2_* bits) for one row size
-template <int ROWU> int t2_attrs(ck_ctx *ctx)
+// lane-per-record streaming kernel (ck_stream2.cuh), variant v (CK_W2_* bits)
+void s2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
 {
-    const u32 d = t2_warps<ROWU>(false) * t2_warp_bytes<ROWU>(false), l = t2_warps<ROWU>(true) * t2_warp_bytes<ROWU>(true);
-    int rc;
-    if ((rc = set_smem(ctx, k_canon_t2<ROWU, 0>, d)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 1>, d)) ||
-        (rc = set_smem(ctx, k_canon_t2<ROWU, 2>, d)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 3>, d)) ||
-        (rc = set_smem(ctx, k_canon_t2<ROWU, 4>, l)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 5>, l)) ||
-        (rc = set_smem(ctx, k_canon_t2<ROWU, 6>, l)) || (rc = set_smem(ctx, k_canon_t2<ROWU, 7>, l))) return rc;
-    return CK_OK;
-}
-template <int ROWU> void t2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
-{
-    const bool ls = a.list != nullptr;
-    const u32 g = t2_ctas<ROWU>() * (u32)ctx->num_sms, th = 32u * t2_warps<ROWU>(ls), sm = t2_warps<ROWU>(ls) * t2_warp_bytes<ROWU>(ls);
-#define CK_T2(V) k_canon_t2<ROWU, V><<<g, th, sm, st>>>(a)
+    const u32 g = 3u * (u32)ctx->num_sms, th = 32u * CK_S2_WARPS, sm = CK_S2_WARPS * CK_S2_WARP_BYTES;
+#define CK_S2(V) k_canon_s2<V><<<g, th, sm, st>>>(a)
     switch (v) {
-    case 0: CK_T2(0); break; case 1: CK_T2(1); break; case 2: CK_T2(2); break; case 3: CK_T2(3); break;
-    case 4: CK_T2(4); break; case 5: CK_T2(5); break; case 6: CK_T2(6); break; default: CK_T2(7);
+    case 0: CK_S2(0); break; case 1: CK_S2(1); break; case 2: CK_S2(2); break; case 3: CK_S2(3); break;
+    case 4: CK_S2(4); break; case 5: CK_S2(5); break; case 6: CK_S2(6); break; default: CK_S2(7);
     }
-#undef CK_T2
+#undef CK_S2
 }
 
 int set_attrs(ck_ctx *ctx)
@@ -202,7 +192,6 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
-    if ((rc = t2_attrs<36>(ctx)) || (rc = t2_attrs<132>(ctx)) || (rc = t2_attrs<260>(ctx)) || (rc = t2_attrs<516>(ctx))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -224,64 +213,83 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     if (io.n == 0) return CK_OK;
     int rc = set_attrs(ctx);
     if (rc) return rc;
-    CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 32 * sizeof(u32), st));
+    CK_CUDA(ctx, cudaMemsetAsync(io.counts, 0, 64 * sizeof(u32), st));
     // a promise of exactly one class lets that class index the records directly (no work lists)
     int only = -1;
     if (class_mask && (class_mask & (class_mask - 1)) == 0)
         for (int c = 0; c < CLS_COUNT; c++) if (class_mask == (1u << c)) only = c;
     const u64 stride = ((u64)io.n + 4) & ~3ull;                // u32 elements per sort buffer
     u32 *k0 = io.lists, *k1 = k0 + stride, *v0 = k1 + stride, *v1 = v0 + stride;
+    if (io.lists_bytes < 16 * stride) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
     ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u};
     k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
     ctx->launches++;
     const u32 *sorted = nullptr;
+    u32 *retry = v0;                                           // direct mode: the sort buffers are free
     if (only < 0) {
         // one index list for the whole batch: classes are contiguous runs, each ordered by length
-        if (io.lists_bytes < 16 * stride) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
         cub::DoubleBuffer<u32> keys(k0, k1), vals(v0, v1);
         void *tmp = v1 + stride;
         size_t tmp_bytes = (size_t)(io.lists_bytes - 16 * stride), need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)io.n, 0, 12, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)io.n, 0, 14, st);
         if (need > tmp_bytes) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
-        CK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, (int)io.n, 0, 12, st));
+        CK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, (int)io.n, 0, 14, st));
         sorted = vals.Current();
+        retry = vals.Alternate();
         k_list_starts<<<1, 32, 0, st>>>(io.counts);
         ctx->launches += 2;
+    }
+    // specialised variants for the resident fast path (packed lengths, both strands, aligned bytes or none): the
+    // lane-per-record streaming kernel; everything else: the run-time-option warp-per-record kernel
+    const bool fastv = io.packed2 && !io.lens && !(io.mode & 1u) && (!io.out || (io.mode & 2u)) && io.out_start && io.out_strand;
+    const u32 lane_classes = (1u << CLS_W2S) | (1u << CLS_W2M) | (1u << CLS_W2L) | (1u << CLS_W2X);
+    auto timed = [&](int slot, cudaEvent_t &e0, cudaEvent_t &e1, bool begin) -> cudaError_t {
+        if (!ctx->timing) return cudaSuccess;
+        if (begin) {
+            cudaError_t e = cudaEventCreate(&e0); if (e != cudaSuccess) return e;
+            e = cudaEventCreate(&e1); if (e != cudaSuccess) return e;
+            return cudaEventRecord(e0, st);
+        }
+        ctx->ev_pairs[slot].push_back(e0); ctx->ev_pairs[slot].push_back(e1);
+        return cudaEventRecord(e1, st);
+    };
+    auto base_args = [&](int c) {
+        CanonArgs a{};
+        a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
+        a.max_n = cls_max_n(c); a.min_n = cls_min_n(c);
+        a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
+        a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
+        a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
+        a.retry = retry; a.retry_counts = io.counts + 32;
+        return a;
+    };
+    const bool lane_run = fastv && (only >= 0 ? ((lane_classes >> only) & 1u) != 0 : (!class_mask || (class_mask & lane_classes)));
+    if (lane_run) {
+        CanonArgs a = base_args(only >= 0 ? only : CLS_W2S);
+        if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
+        else { a.list = sorted; a.count = io.counts + 12; a.n_direct = 0; a.min_n = 1; a.max_n = cls_max_n(CLS_W2X); }
+        const int v = (a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, true));
+        s2_launch(ctx, st, a, v);
+        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, false));
+        ctx->launches++;
     }
     for (int c = 0; c < CLS_COUNT; c++) {
         if (c == CLS_HUGE) continue;
         if (class_mask && !(class_mask & (1u << c))) continue;
-        CanonArgs a{};
-        a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
-        if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
+        CanonArgs a = base_args(c);
+        const bool is_lane_cls = ((lane_classes >> c) & 1u) != 0;
+        if (lane_run && is_lane_cls) { a.list = retry; a.count = io.counts + 32 + c; a.n_direct = 0; }   // what the lane kernel left over
+        else if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
         else { a.list = sorted; a.count = io.counts + c; a.n_direct = 0; }
-        a.max_n = cls_max_n(c);
-        a.min_n = cls_min_n(c);
-        a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
-        a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
-        a.smem_units = kCls[c].bits ? cls_units(c) : 0; a.xglobal = nullptr; a.mode = io.mode;
         const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
         const u32 smem = kCls[c].bits ? cls_smem_bytes(c) : 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (ctx->timing) {
-            CK_CUDA(ctx, cudaEventCreate(&e0)); CK_CUDA(ctx, cudaEventCreate(&e1));
-            CK_CUDA(ctx, cudaEventRecord(e0, st));
-        }
+        CK_CUDA(ctx, timed(c, e0, e1, true));
         switch (c) {
-        case CLS_W2S: case CLS_W2M: case CLS_W2L: case CLS_W2X: {
-            // specialised variants for the resident fast path (packed lengths, both strands, aligned bytes or none):
-            // the lane-per-record kernel; everything else: the run-time-option warp-per-record kernel
-            const bool fast = !a.lens && !(a.mode & 1u) && (!a.out || (a.mode & 2u)) && a.out_start && a.out_strand;
-            const int v = fast ? ((a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0)) : -1;
-            if (v >= 0) {
-                if (c == CLS_W2S) t2_launch<36>(ctx, st, a, v);
-                else if (c == CLS_W2M) t2_launch<132>(ctx, st, a, v);
-                else if (c == CLS_W2L) t2_launch<260>(ctx, st, a, v);
-                else t2_launch<516>(ctx, st, a, v);
-            } else if (c == CLS_W2S) k_canon_w2<true, -1><<<grid, thr, smem, st>>>(a);
-            else k_canon_w2<false, -1><<<grid, thr, smem, st>>>(a);
-            break;
-        }
+        case CLS_W2S: k_canon_w2<true, -1><<<grid, thr, smem, st>>>(a); break;
+        case CLS_W2M: case CLS_W2L: case CLS_W2X: k_canon_w2<false, -1><<<grid, thr, smem, st>>>(a); break;
         case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
         case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;
@@ -289,10 +297,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         case CLS_C8: k_canon_cta<8, false><<<grid, thr, smem, st>>>(a); break;
         case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, st>>>(a); break;
         }
-        if (ctx->timing) {
-            CK_CUDA(ctx, cudaEventRecord(e1, st));
-            ctx->ev_pairs[c].push_back(e0); ctx->ev_pairs[c].push_back(e1);
-        }
+        CK_CUDA(ctx, timed(c, e0, e1, false));
         ctx->launches++;
     }
     CK_CUDA(ctx, cudaGetLastError());
@@ -348,7 +353,8 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
     PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
     k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
-    ctx->launches++;
+    k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records);
+    ctx->launches += 2;
     CanonIO io{};
     io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = s.d_len; io.lane = s.d_lane;
     io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
@@ -441,7 +447,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaMalloc(&s.d_raw, B + 16));
             CK_INIT(cudaMalloc(&s.d_norm, B + 16));
             CK_INIT(cudaMalloc(&s.d_out, B + 16 * R + 64));
-            CK_INIT(cudaMalloc(&s.d_p2, (B / 32 + R + 2) * 8));
+            CK_INIT(cudaMalloc(&s.d_p2, p2_words(B, R) * 8));
             CK_INIT(cudaMalloc(&s.d_off, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_len, (R + 1) * 4));
             CK_INIT(cudaMalloc(&s.d_lane, R + 1));
@@ -451,7 +457,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaMalloc(&s.d_first, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_slotof, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_lists, lists_bytes_for(R)));
-            CK_INIT(cudaMalloc(&s.d_counts, 32 * 4));
+            CK_INIT(cudaMalloc(&s.d_counts, 64 * 4));
             CK_INIT(cudaMallocHost(&s.h_counts, 32 * 4));
             memset(s.h_counts, 0, 32 * 4);
             if (alloc_scratch(ctx, s.scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
@@ -553,15 +559,16 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     cudaError_t e = cudaSuccess;
 #define CK_LB(call) do { if (e == cudaSuccess) e = (call); } while (0)
     CK_LB(cudaMalloc(&d_raw, total + 16)); CK_LB(cudaMalloc(&d_norm, total + 16)); CK_LB(cudaMalloc(&d_out, total + 16));
-    CK_LB(cudaMalloc(&d_p2, (total / 32 + R + 2) * 8)); CK_LB(cudaMalloc(&d_off, (R + 1) * 8));
+    CK_LB(cudaMalloc(&d_p2, p2_words(total, R) * 8)); CK_LB(cudaMalloc(&d_off, (R + 1) * 8));
     CK_LB(cudaMalloc(&d_len, R * 4)); CK_LB(cudaMalloc(&d_lane, R)); CK_LB(cudaMalloc(&d_start, R * 4));
-    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, lists_bytes_for(R))); CK_LB(cudaMalloc(&d_counts, 128));
+    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, lists_bytes_for(R))); CK_LB(cudaMalloc(&d_counts, 256));
     CK_LB(cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice));
     if (total) CK_LB(cudaMemcpy(d_raw, bytes, total, cudaMemcpyHostToDevice));
     if (e == cudaSuccess) {
         PrepareArgs pa{d_raw, d_off, n_records, 0u, d_p2, d_norm, d_len, d_lane};
         k_prepare<<<ctx->num_sms * 8, 256>>>(pa);
-        ctx->launches++;
+        k_extend_packed2<<<(n_records + 255) / 256, 256>>>(d_p2, d_off, d_len, d_lane, n_records);
+        ctx->launches += 2;
         CanonIO io{};
         io.packed2 = d_p2; io.bytes = d_norm; io.offsets = d_off; io.lens = d_len; io.lane = d_lane; io.n = n_records;
         io.mode = mode; io.out = out_bytes ? d_out : nullptr; io.out_start = d_start; io.out_strand = d_strand;
@@ -614,7 +621,7 @@ int ck_canonicalize(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out)
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
 {
     u64 b = 256 + lists_bytes_for(n_records);
-    if (total_bytes) b += (total_bytes / 32 + n_records + 2) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
+    if (total_bytes) b += p2_words(total_bytes, n_records) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
     return (b + 255) & ~255ull;
 }
 uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records) { return 16ull * ((total_bytes >> 4) + n_records) + 16; }
@@ -645,13 +652,14 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     u8 *w = (u8 *)workspace;
     u32 *counts = (u32 *)w; w += 256;
     u32 *lists = (u32 *)w; w += lists_bytes_for(n_records);
-    u64 *p2 = (u64 *)w; w += (total_bytes / 32 + n_records + 2) * 8;
+    u64 *p2 = (u64 *)w; w += p2_words(total_bytes, n_records) * 8;
     u8 *norm = w; w += (total_bytes + 63) & ~63ull;
     u8 *lane = w;
     cudaStream_t st = (cudaStream_t)stream;
     PrepareArgs pa{bytes, U(offsets), n_records, flags & CK_F_NORMALIZE, p2, norm, out_len, lane};
     k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
-    ctx->launches++;
+    k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records);
+    ctx->launches += 2;
     CanonIO io{};
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
     io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
@@ -715,7 +723,7 @@ int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_
     if (!ctx || !out_ms || !out_launches) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     CK_CUDA(ctx, cudaDeviceSynchronize());
     for (u32 c = 0; c < n_classes; c++) { out_ms[c] = 0; out_launches[c] = 0; }
-    for (u32 c = 0; c < (u32)CLS_COUNT + 2; c++) {
+    for (u32 c = 0; c < (u32)CLS_COUNT + 3; c++) {
         std::vector<cudaEvent_t> &v = ctx->ev_pairs[c];
         for (size_t k = 0; k + 1 < v.size(); k += 2) {
             float ms = 0;
@@ -756,8 +764,11 @@ int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_in
 {
     if (!ctx || !offsets_dev || !packed2_dev) return ctx ? fail(ctx, CK_ERR_ARG, "bad synth arguments") : CK_ERR_ARG;
     SynthArgs a{seed, n_records, 0, 0, 0, dup_permille, adversarial_permille, first_index};
-    if (n_records) k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev));
-    ctx->launches++;
+    if (n_records) {
+        k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev));
+        k_extend_packed2<<<(n_records + 255) / 256, 256, 0, (cudaStream_t)stream>>>(U(packed2_dev), U(offsets_dev), nullptr, nullptr, n_records);
+    }
+    ctx->launches += 2;
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }

@@ -1,0 +1,287 @@
+// ck_stream2.cuh -- lane-per-record LMSR + canonical form + XXH3-64 for 2-bit records, streaming form: the hot
+// kernel of every 2-bit configuration of BASELINE.json (1, 2, 5 and the short end of 4).
+//
+// A warp takes 32 records and every lane walks ITS OWN record, so a warp instruction does useful work for 32
+// records and no collective sits on the per-base path (the warp-per-record kernel of ck_warp2.cuh pays ~300 warp
+// instructions of per-record fixed cost for a 325-base record).  Unlike ck_lane2.cuh nothing is staged in shared
+// memory: the packed arena already holds every record 16-byte aligned and followed by its own circular extension
+// (ck_device.cuh, "packed2 arena"), so each lane simply streams its record with 128-bit loads that are issued two
+// iterations ahead (lane-private streaming reaches HBM speed on B200: tools/micro/stream.cu), occupancy is bounded by
+// registers only, and the same kernel serves every record length:
+//   * scan      : 8-mer keys as 16-bit halves (14 funnel shifts + 8 VIMNMX3.U16x2 per 32 rotations).  The reverse
+//                 strand is never materialised: the 48-base block (x0,x1,x2) a step looks at is reverse-complemented
+//                 in registers (BREV + LOP3 per unit), which yields the reverse strand's keys for forward starts
+//                 32t+9 .. 32t+40.  Each lane keeps the two smallest (key, step, strand) triples, so "the minimal
+//                 8-mer is unique" is known exactly.  Only the last step of a record can see positions twice (the
+//                 extension repeats the head); its units are padded in registers (T past base n+7 for the forward
+//                 keys, A past base n+16 for the reverse keys) so that those duplicates can never win;
+//   * locate    : the winning step is replayed once; an XOR / VIMNMX / shift-add chain turns "which of the 32 keys
+//                 equal the minimum" into a bit mask; exactly one valid bit => that rotation is the canonical one;
+//   * ASCII+hash: each lane streams its canonical form in 16-byte chunks (the reverse strand costs nothing extra: a
+//                 per-lane letter table "TGCA" and per-lane PRMT selectors do the complement and the reversal), four
+//                 chunks = one XXH3 stripe per round, eight 64-bit accumulators in registers, the next round's
+//                 units already in flight;
+//   * write     : a round's 64 bytes per lane go through a padded shared-memory stage (the kernel's only shared
+//                 memory) and leave as 128-bit stores in which four consecutive lanes cover 64 contiguous bytes;
+//   * retry     : records a lane cannot finish alone (equal minimal 8-mers, n < 128, the short XXH3 forms of
+//                 n <= 240) are appended to a retry list that the warp- / CTA-per-record kernels work off afterwards.
+// Work lists come sorted by (class, length) (k_classify + radix sort), so the lanes of a warp run the same trip counts.
+#pragma once
+#include "ck_lane2.cuh"
+
+namespace ck {
+
+#define CK_S2_WARPS 8u
+#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u)
+
+__device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint2 ldg64(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ u32 ldg32(const void *p) { return __ldg(reinterpret_cast<const u32 *>(p)); }
+
+template <int V>
+__global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
+{
+    extern __shared__ __align__(16) u32 smem[];
+    constexpr bool want_hash = (V & CK_W2_HASH) != 0, want_out = (V & CK_W2_OUT) != 0, use_list = (V & CK_W2_LIST) != 0;
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const u32 aux = (u32)__cvta_generic_to_shared(smem) + wid * CK_S2_WARP_BYTES;   // output stage
+    const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
+    const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
+    const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
+    const u32 count = use_list ? *a.count : a.n_direct;
+    if (use_list) a.list += a.count[16];
+    const u32 bstride = nw * 32u;
+    const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
+
+    auto fetch_offsets = [&](u32 rec, u32 slot) {
+        cp_async8(offs + 512u * slot, a.offsets + rec);
+        cp_async8(offs + 512u * slot + 8u, a.offsets + rec + 1);
+    };
+    // ---- prologue: offsets of batches 0 and 1, (work lists) record indices of batches 0..2
+    u32 rq = 0;                                                    // work lists: record index two batches ahead
+    {
+        const u32 i0 = gw * 32u + lane, i1 = i0 + bstride, i2 = i1 + bstride;
+        u32 r0 = i0, r1 = i1;
+        if (use_list) {
+            r0 = i0 < count ? a.list[i0] : 0u; r1 = i1 < count ? a.list[i1] : 0u; rq = i2 < count ? a.list[i2] : 0u;
+            sts32(recs, r0); sts32(recs + 128, r1);
+        }
+        if (i0 < count) fetch_offsets(r0, 0);
+        if (i1 < count) fetch_offsets(r1, 1);
+    }
+    u32 kb = 0;                                                    // batch counter of this warp
+    for (u32 b = gw * 32u; b < count; b += bstride, kb++) {
+        const u32 sl = kb & 1u;
+        const u32 idx = b + lane;
+        const bool have = idx < count;
+        cp_async_wait_all();
+        __syncwarp();                                              // the offsets of batches kb and kb + 1 have landed
+        u32 rec = idx; u64 off = 0; u32 n = 0;
+        {
+            const uint4 oe = lds128(offs + 512u * sl);
+            if (use_list) rec = lds32(recs + 128u * (kb % 3u));
+            if (have) { off = ((u64)oe.y << 32) | oe.x; n = oe.z - oe.x; } else rec = 0;
+            const u32 idx2 = idx + 2 * bstride;
+            if (idx2 < count) fetch_offsets(use_list ? rq : idx2, sl);
+            if (use_list) {
+                sts32(recs + 128u * ((kb + 2u) % 3u), rq);
+                const u32 idx3 = idx2 + bstride;
+                rq = idx3 < count ? a.list[idx3] : 0u;
+            }
+        }
+        const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
+        // lane-private fast path: n >= 128 (and the long XXH3 form when a hash is wanted)
+        bool fast = in_class && n >= (want_hash ? 241u : 128u);
+        const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 3 are valid
+        u8 *dst = want_out ? a.out + 16ull * ((off >> 4) + rec) : nullptr;
+        u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
+        u64 h = 0;
+        const u32 nn = fast ? n : 128u;                            // lanes without a fast record walk a dummy geometry
+
+        // ---- scan: the two smallest (8-mer key, step, strand) over all 2n rotations
+        const u32 S1 = ((nn + 31) >> 5) - 1;                       // full steps; step S1 is the padded last one
+        const u32 S1max = __reduce_max_sync(CK_FULL, fast ? S1 : 0u);
+        const u32 qmax = fast ? (S1 + 1) >> 1 : 0u;                // last quad this lane may read (units <= jn + 3)
+        u32 m1 = 0xffffffffu, m2 = 0xffffffffu;
+        const uint2 l01 = ldg64(base + 8 * (fast ? S1 : 0u));      // units of the last step, needed after the loop
+        const u32 l2 = ldg32(base + 8 * (fast ? S1 : 0u) + 8);
+        {
+            uint4 Q = ldg128(base), Q1 = ldg128(base + 16 * min(1u, qmax));
+            u32 rqx = w2_revcomp(Q.x);
+#pragma unroll 1
+            for (u32 i = 0; 2 * i < S1max; i++) {
+                const uint4 Q2 = ldg128(base + 16 * min(i + 2, qmax));       // two iterations ahead
+                const u32 rqy = w2_revcomp(Q.y), rqz = w2_revcomp(Q.z), rqw = w2_revcomp(Q.w), rnx = w2_revcomp(Q1.x);
+                {
+                    const u32 t = 2 * i;
+                    const u32 kf = t2_key_hi(w2_step_min16(Q.x, Q.y, Q.z)), kr = t2_key_hi(w2_step_min16(rqz, rqy, rqx));
+                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;
+                    t2_track(m1, m2, kf | tag);
+                    t2_track(m1, m2, kr | (tag + 1));
+                }
+                {
+                    const u32 t = 2 * i + 1;
+                    const u32 kf = t2_key_hi(w2_step_min16(Q.z, Q.w, Q1.x)), kr = t2_key_hi(w2_step_min16(rnx, rqw, rqz));
+                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;
+                    t2_track(m1, m2, kf | tag);
+                    t2_track(m1, m2, kr | (tag + 1));
+                }
+                Q = Q1; Q1 = Q2; rqx = rnx;
+            }
+        }
+        {   // last step of this lane's record: positions 32 S1 .. n - 1 are new, the rest repeats the head
+            const int dT = (int)nn + 7 - 32 * (int)S1;             // first forward-padded base, relative to unit 2 S1
+            const int dA = dT + 9;                                 // first reverse-padded base
+#define CK_T2_PAD(d) __funnelshift_rc(0xffffffffu, 0u, 2u * (u32)min(max((d), 0), 16))
+            const u32 pT0 = CK_T2_PAD(dT), pT1 = CK_T2_PAD(dT - 16), pT2 = CK_T2_PAD(dT - 32);
+            const u32 pA0 = CK_T2_PAD(dA), pA1 = CK_T2_PAD(dA - 16), pA2 = CK_T2_PAD(dA - 32);
+#undef CK_T2_PAD
+            const u32 kf = t2_key_hi(w2_step_min16(l01.x | pT0, l01.y | pT1, l2 | pT2));
+            const u32 kr = t2_key_hi(w2_step_min16(w2_revcomp(l2 & ~pA2), w2_revcomp(l01.y & ~pA1), w2_revcomp(l01.x & ~pA0)));
+            t2_track(m1, m2, kf | (2 * S1));
+            t2_track(m1, m2, kr | (2 * S1 + 1));
+        }
+        // ---- locate: replay the winning step, find the rotation that carries the minimal 8-mer
+        {
+            const u32 t = fast ? (m1 & 0xffffu) >> 1 : 0u, strand = m1 & 1u;
+            const uint2 x01 = ldg64(base + 8 * t);
+            const u32 x2 = ldg32(base + 8 * t + 8);
+            const u32 y0 = strand ? w2_revcomp(x2) : x01.x, y1 = strand ? w2_revcomp(x01.y) : x01.y;
+            const u32 y2 = strand ? w2_revcomp(x01.x) : x2;
+            const u32 bb = (m1 >> 16) * 0x10001u;
+            u32 nm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const u32 wa = i ? __funnelshift_l(y1, y0, 2 * i) : y0, wb = i ? __funnelshift_l(y2, y1, 2 * i) : y1;
+                nm += __vminu2(wa ^ bb, 0x00010001u) << i;         // bits 16 + i / i: key i / key 8 + i differs
+                nm += __vminu2(wb ^ bb, 0x00010001u) << (i + 8);   // bits 24 + i / 8 + i: key 16 + i / key 24 + i differs
+            }
+            const u32 match = ~__byte_perm(nm, 0, 0x1302);         // bit s: key s of the step equals the minimum
+            // forward: key s is rotation 32 t + s, valid below n.  reverse: key s is forward start 32 t + 40 - s,
+            // valid up to n + 8
+            const int lim = (int)nn - 32 * (int)t;
+            const u32 valid = strand ? (lim >= 32 ? 0xffffffffu : 0xffffffffu << (32 - lim))
+                                     : (lim >= 32 ? 0xffffffffu : (1u << lim) - 1u);
+            const u32 hits = match & valid;
+            const u32 s = __ffs(hits) - 1;
+            int st = strand ? (int)nn - 48 - 32 * (int)t + (int)s : 32 * (int)t + (int)s;
+            if (st < 0) st += (int)nn;
+            os = ((u32)st << 1) | strand;
+            if (((m1 ^ m2) < 0x10000u) || __popc(hits) != 1) fast = false;      // equal minima: the duel path decides
+            if (!fast) os = 0;                                     // keeps the dummy walk below inside the record
+        }
+        // ---- canonical ASCII (+ XXH3-64), lane-private; one stripe (4 chunks of 16 bytes) per round
+        if (want_out || want_hash) {
+            const u32 strand = os & 1u;
+            const u32 T = strand ? 0x41434754u : 0x54474341u;      // "TGCA" / "ACGT"
+            const u32 sa = strand ? 0x5140u : 0x2637u, sb = strand ? 0x7362u : 0x0415u, rot = strand ? 16u : 0u;
+            const int step = strand ? -16 : 16, nstep = strand ? -(int)nn : (int)nn;
+            // forward position of canonical chunk 0: the rotation start, or the mirror of reverse position start
+            int p = strand ? (int)nn - 16 - (int)(os >> 1) : (int)(os >> 1);
+            if (p < 0) p += (int)nn;
+            const int p0 = p;
+            const u32 nchunks = fast ? (nn + 15) >> 4 : 0u;
+            const u32 nfull = fast ? (nn - 1) >> 6 : 0u;           // stripes the stripe loop hashes
+            const u32 rounds = __reduce_max_sync(CK_FULL, (nchunks + 3) >> 2);
+            u64 acc0 = CK_P32_3, acc1 = CK_P64_1, acc2 = CK_P64_2, acc3 = CK_P64_3;
+            u64 acc4 = CK_P64_4, acc5 = CK_P32_2, acc6 = CK_P64_5, acc7 = CK_P32_1;
+            // the four records whose bytes this lane carries out of the stage: records 8 i + (lane >> 2), piece lane & 3
+            u8 *od0 = nullptr, *od1 = nullptr, *od2 = nullptr, *od3 = nullptr;
+            u32 oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
+            if (want_out) {
+                const u64 dp = reinterpret_cast<u64>(dst), pc = 16u * (lane & 3u);
+                const u32 q = lane >> 2;
+                od0 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q) + pc);      oc0 = __shfl_sync(CK_FULL, nchunks, q);
+                od1 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 8) + pc);  oc1 = __shfl_sync(CK_FULL, nchunks, q + 8);
+                od2 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 16) + pc); oc2 = __shfl_sync(CK_FULL, nchunks, q + 16);
+                od3 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 24) + pc); oc3 = __shfl_sync(CK_FULL, nchunks, q + 24);
+            }
+            const u32 ost = aux + 80u * lane;                      // this lane's 64 bytes in the stage (stride 80: no conflicts)
+            const u32 ord = aux + 80u * (lane >> 2) + 16u * (lane & 3u);
+            const u64 *sec = reinterpret_cast<const u64 *>(c_secret);
+            // units of a round's four windows; the next round's are requested before this round's are used
+            u32 wh[4], wl[4], ws[4];
+#define CK_S2_FETCH()                                                                                               \
+            _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                         \
+                const u8 *ad = base + (((u32)p >> 4) << 2);                                                         \
+                wh[k] = ldg32(ad); wl[k] = ldg32(ad + 4); ws[k] = 2u * (u32)p;                                      \
+                p += step;                                                                                          \
+                if ((u32)p >= nn) p -= nstep;                                                                       \
+            }
+            CK_S2_FETCH();
+#pragma unroll 1
+            for (u32 s = 0; s < rounds; s++) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 w = __funnelshift_l(wl[k], wh[k], ws[k]);
+                    w = __funnelshift_l(w, w, rot);
+                    v[k] = t2_ascii16(w, T, sa, sb);
+                }
+                if (s + 1 < rounds) { CK_S2_FETCH(); }
+                if (want_hash && s < nfull) {
+                    const u32 ks = s & 15u;
+                    t2_acc16(acc0, acc1, v[0], sec[ks + 0], sec[ks + 1]);
+                    t2_acc16(acc2, acc3, v[1], sec[ks + 2], sec[ks + 3]);
+                    t2_acc16(acc4, acc5, v[2], sec[ks + 4], sec[ks + 5]);
+                    t2_acc16(acc6, acc7, v[3], sec[ks + 6], sec[ks + 7]);
+                    if (ks == 15u) {                               // a 1024-byte block is complete (s + 1 <= nfull: more input follows)
+#define CK_T2_SCR(A, I) do { A ^= A >> 47; A ^= sec[16 + I]; A *= CK_P32_1; } while (0)
+                        CK_T2_SCR(acc0, 0); CK_T2_SCR(acc1, 1); CK_T2_SCR(acc2, 2); CK_T2_SCR(acc3, 3);
+                        CK_T2_SCR(acc4, 4); CK_T2_SCR(acc5, 5); CK_T2_SCR(acc6, 6); CK_T2_SCR(acc7, 7);
+#undef CK_T2_SCR
+                    }
+                }
+                if (want_out) {
+                    sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);
+                    __syncwarp();
+                    const u32 c = 4 * s + (lane & 3u);
+                    const uint4 g0 = lds128(ord), g1 = lds128(ord + 640), g2 = lds128(ord + 1280), g3 = lds128(ord + 1920);
+                    if (c < oc0) *reinterpret_cast<uint4 *>(od0 + 64 * (size_t)s) = g0;
+                    if (c < oc1) *reinterpret_cast<uint4 *>(od1 + 64 * (size_t)s) = g1;
+                    if (c < oc2) *reinterpret_cast<uint4 *>(od2 + 64 * (size_t)s) = g2;
+                    if (c < oc3) *reinterpret_cast<uint4 *>(od3 + 64 * (size_t)s) = g3;
+                    __syncwarp();
+                }
+            }
+            if (want_hash) {
+                // last stripe: canonical bytes [n - 64, n) = four chunks that start 64 bases before chunk 0
+                p = p0 - 4 * step;
+                if ((u32)p >= nn) p += nstep;
+                CK_S2_FETCH();
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 w = __funnelshift_l(wl[k], wh[k], ws[k]);
+                    w = __funnelshift_l(w, w, rot);
+                    const uint4 vv = t2_ascii16(w, T, sa, sb);
+                    if (k == 0) t2_acc16(acc0, acc1, vv, c_lastsec[0], c_lastsec[1]);
+                    if (k == 1) t2_acc16(acc2, acc3, vv, c_lastsec[2], c_lastsec[3]);
+                    if (k == 2) t2_acc16(acc4, acc5, vv, c_lastsec[4], c_lastsec[5]);
+                    if (k == 3) t2_acc16(acc6, acc7, vv, c_lastsec[6], c_lastsec[7]);
+                }
+                u64 r = (u64)nn * CK_P64_1;
+                r += mul128_fold64(acc0 ^ c_mergesec[0], acc1 ^ c_mergesec[1]);
+                r += mul128_fold64(acc2 ^ c_mergesec[2], acc3 ^ c_mergesec[3]);
+                r += mul128_fold64(acc4 ^ c_mergesec[4], acc5 ^ c_mergesec[5]);
+                r += mul128_fold64(acc6 ^ c_mergesec[6], acc7 ^ c_mergesec[7]);
+                h = xxh3_avalanche(r);
+            }
+#undef CK_S2_FETCH
+        }
+        if (fast) {
+            const u32 start = os >> 1, strand = os & 1u;
+            a.out_start[rec] = strand ? (n - 1 - start) : start;
+            a.out_strand[rec] = (u8)strand;
+            if (want_hash) a.out_hash[rec] = h;
+        } else if (in_class) {
+            // retry list of the record's class: a.retry + (first entry of the class) + (entries so far)
+            const int c = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M : n <= cls_max_n(CLS_W2L) ? CLS_W2L
+                        : n <= cls_max_n(CLS_W2X) ? CLS_W2X : n <= cls_max_n(CLS_C2A) ? CLS_C2A : CLS_C2B;
+            const u32 k = atomicAdd(a.retry_counts + c, 1u);
+            a.retry[a.retry_counts[16 + c] + k] = rec;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace ck

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *o
         const u64 gi = a.first_index + i;
         const u64 off = offsets[i];
         const u32 n = (u32)(offsets[i + 1] - off);
-        u64 *dst = packed2 + ((off >> 5) + i);
+        u64 *dst = packed2 + p2_word(off, i);
         const u64 o = synth_origin(a.seed, gi, a.dup_permille);
         const bool dup = o != gi;
         const u32 W = (n + 31) >> 5;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_unpack2(const u64 *packed2, const u64 *
     for (u32 i = gw; i < n_records; i += nw) {
         const u64 off = offsets[i];
         const u32 n = (u32)(offsets[i + 1] - off);
-        const u64 *src = packed2 + ((off >> 5) + i);
+        const u64 *src = packed2 + p2_word(off, i);
         for (u32 t = lane; t < n; t += 32) {
             u32 c = (reinterpret_cast<const u32 *>(src)[t >> 4] >> (30 - 2 * (t & 15))) & 3u;
             out[off + t] = "ACGT"[c];

@@ -13,17 +13,17 @@ from . import _native as N
 from .core import Context
 
 CLASS_NAMES = ["2bit_le_512", "2bit_le_2048", "2bit_le_65536", "2bit_le_425984", "4bit_le_2048", "4bit_le_212992",
-               "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192"]
+               "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192", "2bit_lane_128_8192"]
 # length range [lo, hi] of each 2-bit class (class_mask bit = index in CLASS_NAMES)
 CLASS_RANGE = {"2bit_le_512": (1, 512), "2bit_le_2048": (513, 2048), "2bit_le_4096": (2049, 4096), "2bit_le_8192": (4097, 8192),
-               "2bit_le_65536": (8193, 65536), "2bit_le_425984": (65537, 425984)}
+               "2bit_le_65536": (8193, 65536), "2bit_le_425984": (65537, 425984), "2bit_lane_128_8192": (1, 8192)}
 
 
 def class_mask_for(lo: int, hi: int) -> int:
     """class_mask promise for 2-bit records with lengths in [lo, hi]."""
     m = 0
     for name, (a, b) in CLASS_RANGE.items():
-        if lo <= b and hi >= a:
+        if "lane" not in name and lo <= b and hi >= a:
             m |= 1 << CLASS_NAMES.index(name)
     return m
 
@@ -55,7 +55,7 @@ def synth_batch(ctx: Context, *, seed: int, first_index: int, n_records: int, ki
     total = C.c_uint64(0)
     ctx._check(ctx._lib.ck_synth_offsets(ctx.handle, _stream(), seed, first_index, n_records, kind, lo, hi,
                                          dup_permille, _p(offsets), C.byref(total)))
-    words = total.value // 32 + n_records + 2
+    words = 2 * ((total.value >> 6) + 2 * n_records + 2)       # ck_device.cuh: p2_words
     packed2 = torch.empty(words, dtype=torch.int64, device=dev)
     ctx._check(ctx._lib.ck_synth_packed2(ctx.handle, _stream(), seed, first_index, n_records, _p(offsets),
                                          dup_permille, adversarial_permille, _p(packed2)))

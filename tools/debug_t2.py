@@ -10,7 +10,7 @@ lo = int(sys.argv[2]) if len(sys.argv) > 2 else 250
 hi = int(sys.argv[3]) if len(sys.argv) > 3 else 400
 mask = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 ctx = circkit_b200.Context(max_batch_bytes=0, max_batch_records=0)
-b = D.synth_batch(ctx, seed=11, first_index=0, n_records=n, kind=0, lo=lo, hi=hi, dup_permille=0, adversarial_permille=0)
+b = D.synth_batch(ctx, seed=11, first_index=0, n_records=n, kind=int(sys.argv[5]) if len(sys.argv) > 5 else 0, lo=lo, hi=hi, dup_permille=0, adversarial_permille=0)
 outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=True, want_hash=True, aligned=True)
 ws = D.Workspace(ctx, n)
 D.canon_packed2(ctx, b, outs, ws, class_mask=mask)
