@@ -37,7 +37,7 @@ __constant__ Tables c_tab;   // single translation unit (ck_lib.cu): defined her
 // ------------------------------------------------------------------ packed2 arena
 // 2-bit arena: A,C,G,T = 0..3, 16 bases per 32-bit unit, first base in the top bits, units in address order.  Record i
 // starts at 16-byte granule (offsets[i] >> 6) + 2 i (so every record can be streamed with aligned 128-bit loads), and
-// its units 0 .. (n >> 4) + 3 hold the bases S[b mod n], i.e. the record is followed by its own circular extension
+// its units 0 .. (n >> 4) + 4 hold the bases S[b mod n], i.e. the record is followed by its own circular extension
 // (k_extend_packed2): a 16-base window that starts anywhere in the record never needs wrap logic.
 __host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec) { return 2 * ((off >> 6) + 2 * rec); }     // u64 word index
 __host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records) { return 2 * ((total >> 6) + 2 * n_records + 2); }

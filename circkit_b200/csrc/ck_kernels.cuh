@@ -335,7 +335,7 @@ __global__ void k_list_starts(u32 *counts)
     }
 }
 
-// k_extend_packed2: append the circular extension to every packed record (units jn .. jn + 3, jn = n >> 4; the
+// k_extend_packed2: append the circular extension to every packed record (units jn .. jn + 4, jn = n >> 4; the
 // partial unit jn keeps its real bases).  One thread per record; runs after the packer (k_prepare / k_synth_packed2).
 __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane, u32 n_records)
 {
@@ -347,14 +347,15 @@ __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 
     if (n == 0) return;
     u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i));
     const u32 jn = n >> 4, rem = n & 15u;
-    u32 e[4];
-    if (n >= 64) {
-        const u32 u0 = U[0], u1 = U[1], u2 = U[2], u3 = U[3], uj = U[jn];
+    u32 e[5];
+    if (n >= 80) {
+        const u32 u0 = U[0], u1 = U[1], u2 = U[2], u3 = U[3], u4 = U[4], uj = U[jn];
         const u32 sh = 32u - 2u * rem;
         e[0] = (uj & ~(0xffffffffu >> (2 * rem))) | (u0 >> (2 * rem));
         e[1] = __funnelshift_lc(u1, u0, sh); e[2] = __funnelshift_lc(u2, u1, sh); e[3] = __funnelshift_lc(u3, u2, sh);
+        e[4] = __funnelshift_lc(u4, u3, sh);
     } else {
-        for (u32 k = 0; k < 4; k++) {
+        for (u32 k = 0; k < 5; k++) {
             u32 v = 0;
             for (u32 b = 0; b < 16; b++) {
                 const u32 t = (16 * (jn + k) + b) % n;
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 
             e[k] = v;
         }
     }
-    U[jn] = e[0]; U[jn + 1] = e[1]; U[jn + 2] = e[2]; U[jn + 3] = e[3];
+    for (u32 k = 0; k < 5; k++) U[jn + k] = e[k];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -32,11 +32,21 @@
 namespace ck {
 
 #define CK_S2_WARPS 8u
-#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u)
+#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u + 512u)
 
 __device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+// same load as an asm volatile statement: the compiler must leave it where it is written (it would otherwise sink a
+// load that is only used in the next unrolled loop instance into that instance, undoing the software pipeline)
+__device__ __forceinline__ uint4 ldg128_here(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint2 ldg64(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
 __device__ __forceinline__ u32 ldg32(const void *p) { return __ldg(reinterpret_cast<const u32 *>(p)); }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int V>
 __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
@@ -89,10 +99,20 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                 rq = idx3 < count ? a.list[idx3] : 0u;
             }
         }
+        if (idx + bstride < count) {                               // next batch: the head of its records -> L2
+            const uint4 oe = lds128(offs + 512u * (sl ^ 1u));
+            const u32 rec1 = use_list ? lds32(recs + 128u * ((kb + 1u) % 3u)) : idx + bstride;
+            const u8 *nb = arena + 8ull * p2_word(((u64)oe.y << 32) | oe.x, rec1);
+            const u32 bytes = (oe.z - oe.x) >> 2;
+            prefetch_l2(nb);
+            if (bytes > 64) prefetch_l2(nb + 64);
+            if (bytes > 128) prefetch_l2(nb + 128);
+            if (bytes > 192) prefetch_l2(nb + 192);
+        }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         // lane-private fast path: n >= 128 (and the long XXH3 form when a hash is wanted)
         bool fast = in_class && n >= (want_hash ? 241u : 128u);
-        const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 3 are valid
+        const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 4 are valid
         u8 *dst = want_out ? a.out + 16ull * ((off >> 4) + rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
         u64 h = 0;
@@ -106,28 +126,43 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
         const uint2 l01 = ldg64(base + 8 * (fast ? S1 : 0u));      // units of the last step, needed after the loop
         const u32 l2 = ldg32(base + 8 * (fast ? S1 : 0u) + 8);
         {
-            uint4 Q = ldg128(base), Q1 = ldg128(base + 16 * min(1u, qmax));
-            u32 rqx = w2_revcomp(Q.x);
-#pragma unroll 1
-            for (u32 i = 0; 2 * i < S1max; i++) {
-                const uint4 Q2 = ldg128(base + 16 * min(i + 2, qmax));       // two iterations ahead
-                const u32 rqy = w2_revcomp(Q.y), rqz = w2_revcomp(Q.z), rqw = w2_revcomp(Q.w), rnx = w2_revcomp(Q1.x);
-                {
-                    const u32 t = 2 * i;
-                    const u32 kf = t2_key_hi(w2_step_min16(Q.x, Q.y, Q.z)), kr = t2_key_hi(w2_step_min16(rqz, rqy, rqx));
-                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;
-                    t2_track(m1, m2, kf | tag);
-                    t2_track(m1, m2, kr | (tag + 1));
-                }
-                {
-                    const u32 t = 2 * i + 1;
-                    const u32 kf = t2_key_hi(w2_step_min16(Q.z, Q.w, Q1.x)), kr = t2_key_hi(w2_step_min16(rnx, rqw, rqz));
-                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;
-                    t2_track(m1, m2, kf | tag);
-                    t2_track(m1, m2, kr | (tag + 1));
-                }
-                Q = Q1; Q1 = Q2; rqx = rnx;
+            // three quads in flight; the loop is unrolled three times so that they rotate by renaming (a register
+            // move of a quad would wait for its load)
+            uint4 QA = ldg128_here(base), QB = ldg128_here(base + 16 * min(1u, qmax)), QC;
+            u32 rqx = w2_revcomp(QA.x);
+            const u32 iters = (S1max + 1) >> 1;
+#define CK_S2_SCAN(Q, Q1, Q2)                                                                                          \
+            {                                                                                                          \
+                Q2 = ldg128_here(base + 16 * min(i + 2, qmax));                                                        \
+                if ((i & 3u) == 0) prefetch_l2(base + 16 * min(i + 16, qmax));                                         \
+                const u32 rqy = w2_revcomp(Q.y), rqz = w2_revcomp(Q.z), rqw = w2_revcomp(Q.w), rnx = w2_revcomp(Q1.x); \
+                {                                                                                                      \
+                    const u32 t = 2 * i;                                                                               \
+                    const u32 kf = t2_key_hi(w2_step_min16(Q.x, Q.y, Q.z)), kr = t2_key_hi(w2_step_min16(rqz, rqy, rqx)); \
+                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;                                                    \
+                    t2_track(m1, m2, kf | tag);                                                                        \
+                    t2_track(m1, m2, kr | (tag + 1));                                                                  \
+                }                                                                                                      \
+                {                                                                                                      \
+                    const u32 t = 2 * i + 1;                                                                           \
+                    const u32 kf = t2_key_hi(w2_step_min16(Q.z, Q.w, Q1.x)), kr = t2_key_hi(w2_step_min16(rnx, rqw, rqz)); \
+                    const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;                                                    \
+                    t2_track(m1, m2, kf | tag);                                                                        \
+                    t2_track(m1, m2, kr | (tag + 1));                                                                  \
+                }                                                                                                      \
+                rqx = rnx;                                                                                             \
+                if (++i >= iters) break;                                                                               \
             }
+            if (iters) {
+                u32 i = 0;
+#pragma unroll 1
+                for (;;) {
+                    CK_S2_SCAN(QA, QB, QC)
+                    CK_S2_SCAN(QB, QC, QA)
+                    CK_S2_SCAN(QC, QA, QB)
+                }
+            }
+#undef CK_S2_SCAN
         }
         {   // last step of this lane's record: positions 32 S1 .. n - 1 are new, the rest repeats the head
             const int dT = (int)nn + 7 - 32 * (int)S1;             // first forward-padded base, relative to unit 2 S1
@@ -170,55 +205,71 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
             if (((m1 ^ m2) < 0x10000u) || __popc(hits) != 1) fast = false;      // equal minima: the duel path decides
             if (!fast) os = 0;                                     // keeps the dummy walk below inside the record
         }
-        // ---- canonical ASCII (+ XXH3-64), lane-private; one stripe (4 chunks of 16 bytes) per round
+        // ---- canonical ASCII (+ XXH3-64), lane-private; one stripe (4 chunks of 16 bytes) per round.
+        //      A round reads the 64 + 15 bases that start at forward position B (two aligned 128-bit loads; the in-arena
+        //      extension makes the read linear): windows B, B+16, B+32, B+48.  Forward strand: chunk k = window k and
+        //      B advances by 64; reverse strand: chunk k = reverse complement of window 3 - k and B retreats by 64.
         if (want_out || want_hash) {
             const u32 strand = os & 1u;
             const u32 T = strand ? 0x41434754u : 0x54474341u;      // "TGCA" / "ACGT"
             const u32 sa = strand ? 0x5140u : 0x2637u, sb = strand ? 0x7362u : 0x0415u, rot = strand ? 16u : 0u;
-            const int step = strand ? -16 : 16, nstep = strand ? -(int)nn : (int)nn;
+            const int step = strand ? -64 : 64, nstep = strand ? -(int)nn : (int)nn;
             // forward position of canonical chunk 0: the rotation start, or the mirror of reverse position start
-            int p = strand ? (int)nn - 16 - (int)(os >> 1) : (int)(os >> 1);
-            if (p < 0) p += (int)nn;
-            const int p0 = p;
+            int p0 = strand ? (int)nn - 16 - (int)(os >> 1) : (int)(os >> 1);
+            if (p0 < 0) p0 += (int)nn;
+            int B = strand ? p0 - 48 : p0;                         // lowest window of round 0
+            if (B < 0) B += (int)nn;
             const u32 nchunks = fast ? (nn + 15) >> 4 : 0u;
             const u32 nfull = fast ? (nn - 1) >> 6 : 0u;           // stripes the stripe loop hashes
             const u32 rounds = __reduce_max_sync(CK_FULL, (nchunks + 3) >> 2);
             u64 acc0 = CK_P32_3, acc1 = CK_P64_1, acc2 = CK_P64_2, acc3 = CK_P64_3;
             u64 acc4 = CK_P64_4, acc5 = CK_P32_2, acc6 = CK_P64_5, acc7 = CK_P32_1;
-            // the four records whose bytes this lane carries out of the stage: records 8 i + (lane >> 2), piece lane & 3
-            u8 *od0 = nullptr, *od1 = nullptr, *od2 = nullptr, *od3 = nullptr;
-            u32 oc0 = 0, oc1 = 0, oc2 = 0, oc3 = 0;
+            // (destination, chunks) of every record of the batch, read back by the lanes that carry its bytes out of the stage
+            const u32 dsc = aux + CK_T2_AUX_BYTES + 1024u + 384u;
             if (want_out) {
-                const u64 dp = reinterpret_cast<u64>(dst), pc = 16u * (lane & 3u);
-                const u32 q = lane >> 2;
-                od0 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q) + pc);      oc0 = __shfl_sync(CK_FULL, nchunks, q);
-                od1 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 8) + pc);  oc1 = __shfl_sync(CK_FULL, nchunks, q + 8);
-                od2 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 16) + pc); oc2 = __shfl_sync(CK_FULL, nchunks, q + 16);
-                od3 = reinterpret_cast<u8 *>(__shfl_sync(CK_FULL, dp, q + 24) + pc); oc3 = __shfl_sync(CK_FULL, nchunks, q + 24);
+                const u64 dp = reinterpret_cast<u64>(dst);
+                sts128(dsc + 16u * lane, make_uint4((u32)dp, (u32)(dp >> 32), nchunks, 0u));
+                __syncwarp();
             }
             const u32 ost = aux + 80u * lane;                      // this lane's 64 bytes in the stage (stride 80: no conflicts)
             const u32 ord = aux + 80u * (lane >> 2) + 16u * (lane & 3u);
             const u64 *sec = reinterpret_cast<const u64 *>(c_secret);
-            // units of a round's four windows; the next round's are requested before this round's are used
-            u32 wh[4], wl[4], ws[4];
+            // the two quads of a round and its (unit offset, bit shift); the next round's are requested before this round's are used
+            uint4 XA, XB; u32 xa, xs;
 #define CK_S2_FETCH()                                                                                               \
-            _Pragma("unroll") for (int k = 0; k < 4; k++) {                                                         \
-                const u8 *ad = base + (((u32)p >> 4) << 2);                                                         \
-                wh[k] = ldg32(ad); wl[k] = ldg32(ad + 4); ws[k] = 2u * (u32)p;                                      \
-                p += step;                                                                                          \
-                if ((u32)p >= nn) p -= nstep;                                                                       \
+            {                                                                                                       \
+                const u8 *ad = base + (((u32)B >> 6) << 4);                                                         \
+                XA = ldg128(ad); XB = ldg128(ad + 16);                                                              \
+                xa = ((u32)B >> 4) & 3u; xs = 2u * (u32)B;                                                          \
+                B += step;                                                                                          \
+                if ((u32)B >= nn) B -= nstep;                                                                       \
+            }
+            // four canonical 16-base windows of the fetched round, in chunk order
+#define CK_S2_WINDOWS(W)                                                                                            \
+            {                                                                                                       \
+                const bool a2 = (xa & 2u) != 0, a1 = (xa & 1u) != 0;                                                \
+                const u32 y0 = a2 ? XA.z : XA.x, y1 = a2 ? XA.w : XA.y, y2 = a2 ? XB.x : XA.z, y3 = a2 ? XB.y : XA.w; \
+                const u32 y4 = a2 ? XB.z : XB.x, y5 = a2 ? XB.w : XB.y;                                             \
+                const u32 u0 = a1 ? y1 : y0, u1 = a1 ? y2 : y1, u2 = a1 ? y3 : y2, u3 = a1 ? y4 : y3, u4 = a1 ? y5 : y4; \
+                const u32 w0 = __funnelshift_l(u1, u0, xs), w1 = __funnelshift_l(u2, u1, xs);                       \
+                const u32 w2 = __funnelshift_l(u3, u2, xs), w3 = __funnelshift_l(u4, u3, xs);                       \
+                W[0] = strand ? w3 : w0; W[1] = strand ? w2 : w1; W[2] = strand ? w1 : w2; W[3] = strand ? w0 : w3; \
             }
             CK_S2_FETCH();
 #pragma unroll 1
             for (u32 s = 0; s < rounds; s++) {
                 uint4 v[4];
+                {
+                    u32 W[4];
+                    CK_S2_WINDOWS(W);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 w = __funnelshift_l(wl[k], wh[k], ws[k]);
-                    w = __funnelshift_l(w, w, rot);
-                    v[k] = t2_ascii16(w, T, sa, sb);
+                    for (int k = 0; k < 4; k++) v[k] = t2_ascii16(__funnelshift_l(W[k], W[k], rot), T, sa, sb);
                 }
-                if (s + 1 < rounds) { CK_S2_FETCH(); }
+                if (s + 1 < rounds) {
+                    CK_S2_FETCH();
+                    const int pa = B + 3 * step;                   // four rounds ahead, same direction (inside the record only)
+                    if ((u32)pa < nn) prefetch_l2(base + (((u32)pa >> 6) << 4));
+                }
                 if (want_hash && s < nfull) {
                     const u32 ks = s & 15u;
                     t2_acc16(acc0, acc1, v[0], sec[ks + 0], sec[ks + 1]);
@@ -233,31 +284,37 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                     }
                 }
                 if (want_out) {
+                    uint4 d[4];
+#pragma unroll
+                    for (u32 i = 0; i < 4; i++) d[i] = lds128(dsc + 16u * (8u * i + (lane >> 2)));   // records 8 i + (lane >> 2)
                     sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);
                     __syncwarp();
                     const u32 c = 4 * s + (lane & 3u);
-                    const uint4 g0 = lds128(ord), g1 = lds128(ord + 640), g2 = lds128(ord + 1280), g3 = lds128(ord + 1920);
-                    if (c < oc0) *reinterpret_cast<uint4 *>(od0 + 64 * (size_t)s) = g0;
-                    if (c < oc1) *reinterpret_cast<uint4 *>(od1 + 64 * (size_t)s) = g1;
-                    if (c < oc2) *reinterpret_cast<uint4 *>(od2 + 64 * (size_t)s) = g2;
-                    if (c < oc3) *reinterpret_cast<uint4 *>(od3 + 64 * (size_t)s) = g3;
+                    uint4 g[4];
+#pragma unroll
+                    for (u32 i = 0; i < 4; i++) g[i] = lds128(ord + 640u * i);                       // piece lane & 3
+#pragma unroll
+                    for (u32 i = 0; i < 4; i++)
+                        if (c < d[i].z) *reinterpret_cast<uint4 *>(((u64)d[i].y << 32 | d[i].x) + 64ull * s + 16u * (lane & 3u)) = g[i];
                     __syncwarp();
                 }
             }
             if (want_hash) {
-                // last stripe: canonical bytes [n - 64, n) = four chunks that start 64 bases before chunk 0
-                p = p0 - 4 * step;
-                if ((u32)p >= nn) p += nstep;
+                // last stripe: canonical bytes [n - 64, n) = the four chunks that end where chunk 0 starts
+                B = strand ? p0 + 16 : p0 - 64;
+                if ((u32)B >= nn) B += nstep;
                 CK_S2_FETCH();
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 w = __funnelshift_l(wl[k], wh[k], ws[k]);
-                    w = __funnelshift_l(w, w, rot);
-                    const uint4 vv = t2_ascii16(w, T, sa, sb);
-                    if (k == 0) t2_acc16(acc0, acc1, vv, c_lastsec[0], c_lastsec[1]);
-                    if (k == 1) t2_acc16(acc2, acc3, vv, c_lastsec[2], c_lastsec[3]);
-                    if (k == 2) t2_acc16(acc4, acc5, vv, c_lastsec[4], c_lastsec[5]);
-                    if (k == 3) t2_acc16(acc6, acc7, vv, c_lastsec[6], c_lastsec[7]);
+                u32 W[4];
+                CK_S2_WINDOWS(W);
+                {
+                    const uint4 v0 = t2_ascii16(__funnelshift_l(W[0], W[0], rot), T, sa, sb);
+                    t2_acc16(acc0, acc1, v0, c_lastsec[0], c_lastsec[1]);
+                    const uint4 v1 = t2_ascii16(__funnelshift_l(W[1], W[1], rot), T, sa, sb);
+                    t2_acc16(acc2, acc3, v1, c_lastsec[2], c_lastsec[3]);
+                    const uint4 v2 = t2_ascii16(__funnelshift_l(W[2], W[2], rot), T, sa, sb);
+                    t2_acc16(acc4, acc5, v2, c_lastsec[4], c_lastsec[5]);
+                    const uint4 v3 = t2_ascii16(__funnelshift_l(W[3], W[3], rot), T, sa, sb);
+                    t2_acc16(acc6, acc7, v3, c_lastsec[6], c_lastsec[7]);
                 }
                 u64 r = (u64)nn * CK_P64_1;
                 r += mul128_fold64(acc0 ^ c_mergesec[0], acc1 ^ c_mergesec[1]);
@@ -267,6 +324,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                 h = xxh3_avalanche(r);
             }
 #undef CK_S2_FETCH
+#undef CK_S2_WINDOWS
         }
         if (fast) {
             const u32 start = os >> 1, strand = os & 1u;

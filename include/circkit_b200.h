@@ -100,7 +100,7 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
  * and nothing synchronises; call ck_dev_check() once a stream's work matters.
  * packed2: 2-bit arena, A,C,G,T = 0..3, 16 bases per 32-bit unit with the first base in the top bits, units in
  * address order; record i starts at byte 16 * ((offsets[i] >> 6) + 2 i) and is followed by its own circular extension
- * (units 0 .. (n >> 4) + 3 hold the bases S[b mod n]); the arena holds 2 * (total/64 + 2 n_records + 2) 64-bit words.  class_mask: 0 = any record; else a promise about the batch (bit c set =
+ * (units 0 .. (n >> 4) + 4 hold the bases S[b mod n]); the arena holds 2 * (total/64 + 2 n_records + 2) 64-bit words.  class_mask: 0 = any record; else a promise about the batch (bit c set =
  * length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
  * records outside the promise are reported by ck_dev_check(), never silently dropped. */
 #define CK_CLASS_2BIT_LE_512 (1u << 0)
