@@ -306,9 +306,11 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
         return;
     }
     if (cls >= 0) {
-        // key = (rank of the class in list order) : (length on a 1/32-octave log scale)
+        // key = (rank of the class in list order) : (length on a 1/4-octave log scale: lanes of a warp differ by < 19 % in
+        // length, and a bin is dense enough that its consecutive members sit close together in the arenas; measured on
+        // config 2: 1/32 octave 9.7 ms, 1/8 octave 8.6 ms, 1/4 octave 8.4 ms)
         const u32 msb = 31u - __clz(n | 1u);
-        const u32 bin = (msb << 5) | (((n << (31u - msb)) >> 26) & 31u);
+        const u32 bin = (msb << 5) | ((((n << (31u - msb)) >> 29) & 3u) << 3);
         a.keys[i] = (cls_rank(cls) << 10) | bin; a.vals[i] = i;
     }
     // warp-aggregated counting, one atomic per (warp, class present)

@@ -176,7 +176,7 @@ template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
 // lane-per-record streaming kernel (ck_stream2.cuh), variant v (CK_W2_* bits)
 void s2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
 {
-    const u32 g = 3u * (u32)ctx->num_sms, th = 32u * CK_S2_WARPS, sm = CK_S2_WARPS * CK_S2_WARP_BYTES;
+    const u32 g = 2u * (u32)ctx->num_sms, th = 32u * CK_S2_WARPS, sm = CK_S2_WARPS * CK_S2_WARP_BYTES;
 #define CK_S2(V) k_canon_s2<V><<<g, th, sm, st>>>(a)
     switch (v) {
     case 0: CK_S2(0); break; case 1: CK_S2(1); break; case 2: CK_S2(2); break; case 3: CK_S2(3); break;
@@ -192,6 +192,10 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_cta<2, false>, cls_smem_bytes(CLS_C2B)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<4, false>, cls_smem_bytes(CLS_C4)))) return rc;
     if ((rc = set_smem(ctx, k_canon_cta<8, false>, cls_smem_bytes(CLS_C8)))) return rc;
+    const u32 s2 = CK_S2_WARPS * CK_S2_WARP_BYTES;
+    if ((rc = set_smem(ctx, k_canon_s2<0>, s2)) || (rc = set_smem(ctx, k_canon_s2<1>, s2)) || (rc = set_smem(ctx, k_canon_s2<2>, s2)) ||
+        (rc = set_smem(ctx, k_canon_s2<3>, s2)) || (rc = set_smem(ctx, k_canon_s2<4>, s2)) || (rc = set_smem(ctx, k_canon_s2<5>, s2)) ||
+        (rc = set_smem(ctx, k_canon_s2<6>, s2)) || (rc = set_smem(ctx, k_canon_s2<7>, s2))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }

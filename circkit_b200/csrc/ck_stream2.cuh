@@ -32,7 +32,7 @@
 namespace ck {
 
 #define CK_S2_WARPS 8u
-#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u + 512u)
+#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u + 512u + 2560u)
 
 __device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 // same load as an asm volatile statement: the compiler must leave it where it is written (it would otherwise sink a
@@ -46,10 +46,14 @@ __device__ __forceinline__ uint4 ldg128_here(const void *p)
 __device__ __forceinline__ uint2 ldg64(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
 __device__ __forceinline__ u32 ldg32(const void *p) { return __ldg(reinterpret_cast<const u32 *>(p)); }
 
+__device__ __forceinline__ void cp_async16(u32 dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int V>
-__global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
+__global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
 {
     extern __shared__ __align__(16) u32 smem[];
     constexpr bool want_hash = (V & CK_W2_HASH) != 0, want_out = (V & CK_W2_OUT) != 0, use_list = (V & CK_W2_LIST) != 0;
@@ -57,11 +61,24 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
     const u32 aux = (u32)__cvta_generic_to_shared(smem) + wid * CK_S2_WARP_BYTES;   // output stage
     const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
     const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
+    const u32 head = aux + CK_T2_AUX_BYTES + 1024u + 384u + 512u + 80u * lane;   // first three quads + last-step units of this lane's record
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     const u32 count = use_list ? *a.count : a.n_direct;
     if (use_list) a.list += a.count[16];
     const u32 bstride = nw * 32u;
     const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
+    // request the head of a record (quads 0..2 and the three units of its last scan step) into this lane's head slot: issued
+    // one batch ahead, so no lane waits for the first touch of its record
+    auto fetch_head = [&](u64 off1, u32 n1, u32 rec1) {
+        const u8 *nb = arena + 8ull * p2_word(off1, rec1);
+        const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
+        cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32);
+        cp_async8(head + 48, nb + 8 * s1); cp_async8(head + 56, nb + 8 * s1 + 8);
+        const u32 bytes = n1 >> 2;                                 // the rest of a short record -> L2
+        if (bytes > 64) prefetch_l2(nb + 64);
+        if (bytes > 128) prefetch_l2(nb + 128);
+        if (bytes > 192) prefetch_l2(nb + 192);
+    };
 
     auto fetch_offsets = [&](u32 rec, u32 slot) {
         cp_async8(offs + 512u * slot, a.offsets + rec);
@@ -78,6 +95,12 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
         }
         if (i0 < count) fetch_offsets(r0, 0);
         if (i1 < count) fetch_offsets(r1, 1);
+        cp_async_wait_all();
+        __syncwarp();
+        if (i0 < count) {
+            const uint4 oe = lds128(offs);
+            fetch_head(((u64)oe.y << 32) | oe.x, oe.z - oe.x, r0);
+        }
     }
     u32 kb = 0;                                                    // batch counter of this warp
     for (u32 b = gw * 32u; b < count; b += bstride, kb++) {
@@ -99,15 +122,12 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                 rq = idx3 < count ? a.list[idx3] : 0u;
             }
         }
-        if (idx + bstride < count) {                               // next batch: the head of its records -> L2
+        // this batch's record heads (requested one batch ago), then the request for the next batch's
+        const uint4 H0 = lds128(head), H1 = lds128(head + 16), H2 = lds128(head + 32), HT = lds128(head + 48);
+        if (idx + bstride < count) {
             const uint4 oe = lds128(offs + 512u * (sl ^ 1u));
             const u32 rec1 = use_list ? lds32(recs + 128u * ((kb + 1u) % 3u)) : idx + bstride;
-            const u8 *nb = arena + 8ull * p2_word(((u64)oe.y << 32) | oe.x, rec1);
-            const u32 bytes = (oe.z - oe.x) >> 2;
-            prefetch_l2(nb);
-            if (bytes > 64) prefetch_l2(nb + 64);
-            if (bytes > 128) prefetch_l2(nb + 128);
-            if (bytes > 192) prefetch_l2(nb + 192);
+            fetch_head(((u64)oe.y << 32) | oe.x, oe.z - oe.x, rec1);
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         // lane-private fast path: n >= 128 (and the long XXH3 form when a hash is wanted)
@@ -123,17 +143,17 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
         const u32 S1max = __reduce_max_sync(CK_FULL, fast ? S1 : 0u);
         const u32 qmax = fast ? (S1 + 1) >> 1 : 0u;                // last quad this lane may read (units <= jn + 3)
         u32 m1 = 0xffffffffu, m2 = 0xffffffffu;
-        const uint2 l01 = ldg64(base + 8 * (fast ? S1 : 0u));      // units of the last step, needed after the loop
-        const u32 l2 = ldg32(base + 8 * (fast ? S1 : 0u) + 8);
+        const uint2 l01 = make_uint2(HT.x, HT.y);                  // units of the last step, needed after the loop
+        const u32 l2 = HT.z;
         {
-            // three quads in flight; the loop is unrolled three times so that they rotate by renaming (a register
-            // move of a quad would wait for its load)
-            uint4 QA = ldg128_here(base), QB = ldg128_here(base + 16 * min(1u, qmax)), QC;
+            // four quads in flight (loads run three iterations ahead); the loop is unrolled four times so that they rotate
+            // by renaming (a register move of a quad would wait for its load)
+            uint4 QA = H0, QB = H1, QC = H2, QD;
             u32 rqx = w2_revcomp(QA.x);
             const u32 iters = (S1max + 1) >> 1;
 #define CK_S2_SCAN(Q, Q1, Q2)                                                                                          \
             {                                                                                                          \
-                Q2 = ldg128_here(base + 16 * min(i + 2, qmax));                                                        \
+                Q2 = ldg128_here(base + 16 * min(i + 3, qmax));                                                        \
                 if ((i & 3u) == 0) prefetch_l2(base + 16 * min(i + 16, qmax));                                         \
                 const u32 rqy = w2_revcomp(Q.y), rqz = w2_revcomp(Q.z), rqw = w2_revcomp(Q.w), rnx = w2_revcomp(Q1.x); \
                 {                                                                                                      \
@@ -157,9 +177,10 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                 u32 i = 0;
 #pragma unroll 1
                 for (;;) {
-                    CK_S2_SCAN(QA, QB, QC)
+                    CK_S2_SCAN(QA, QB, QD)
                     CK_S2_SCAN(QB, QC, QA)
-                    CK_S2_SCAN(QC, QA, QB)
+                    CK_S2_SCAN(QC, QD, QB)
+                    CK_S2_SCAN(QD, QA, QC)
                 }
             }
 #undef CK_S2_SCAN
@@ -234,18 +255,19 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
             const u32 ost = aux + 80u * lane;                      // this lane's 64 bytes in the stage (stride 80: no conflicts)
             const u32 ord = aux + 80u * (lane >> 2) + 16u * (lane & 3u);
             const u64 *sec = reinterpret_cast<const u64 *>(c_secret);
-            // the two quads of a round and its (unit offset, bit shift); the next round's are requested before this round's are used
-            uint4 XA, XB; u32 xa, xs;
-#define CK_S2_FETCH()                                                                                               \
+            // the two quads of a round and its (unit offset, bit shift), in two register sets: the next round's are requested
+            // into the other set before this round's are used (the loop is unrolled twice, so nothing is ever moved)
+            uint4 XA0, XB0, XA1, XB1; u32 xa0, xs0, xa1, xs1;
+#define CK_S2_FETCH(XA, XB, xa, xs)                                                                                 \
             {                                                                                                       \
                 const u8 *ad = base + (((u32)B >> 6) << 4);                                                         \
-                XA = ldg128(ad); XB = ldg128(ad + 16);                                                              \
+                XA = ldg128_here(ad); XB = ldg128_here(ad + 16);                                                    \
                 xa = ((u32)B >> 4) & 3u; xs = 2u * (u32)B;                                                          \
                 B += step;                                                                                          \
                 if ((u32)B >= nn) B -= nstep;                                                                       \
             }
             // four canonical 16-base windows of the fetched round, in chunk order
-#define CK_S2_WINDOWS(W)                                                                                            \
+#define CK_S2_WINDOWS(W, XA, XB, xa, xs)                                                                            \
             {                                                                                                       \
                 const bool a2 = (xa & 2u) != 0, a1 = (xa & 1u) != 0;                                                \
                 const u32 y0 = a2 ? XA.z : XA.x, y1 = a2 ? XA.w : XA.y, y2 = a2 ? XB.x : XA.z, y3 = a2 ? XB.y : XA.w; \
@@ -255,57 +277,62 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
                 const u32 w2 = __funnelshift_l(u3, u2, xs), w3 = __funnelshift_l(u4, u3, xs);                       \
                 W[0] = strand ? w3 : w0; W[1] = strand ? w2 : w1; W[2] = strand ? w1 : w2; W[3] = strand ? w0 : w3; \
             }
-            CK_S2_FETCH();
-#pragma unroll 1
-            for (u32 s = 0; s < rounds; s++) {
-                uint4 v[4];
-                {
-                    u32 W[4];
-                    CK_S2_WINDOWS(W);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) v[k] = t2_ascii16(__funnelshift_l(W[k], W[k], rot), T, sa, sb);
-                }
-                if (s + 1 < rounds) {
-                    CK_S2_FETCH();
-                    const int pa = B + 3 * step;                   // four rounds ahead, same direction (inside the record only)
-                    if ((u32)pa < nn) prefetch_l2(base + (((u32)pa >> 6) << 4));
-                }
-                if (want_hash && s < nfull) {
-                    const u32 ks = s & 15u;
-                    t2_acc16(acc0, acc1, v[0], sec[ks + 0], sec[ks + 1]);
-                    t2_acc16(acc2, acc3, v[1], sec[ks + 2], sec[ks + 3]);
-                    t2_acc16(acc4, acc5, v[2], sec[ks + 4], sec[ks + 5]);
-                    t2_acc16(acc6, acc7, v[3], sec[ks + 6], sec[ks + 7]);
-                    if (ks == 15u) {                               // a 1024-byte block is complete (s + 1 <= nfull: more input follows)
 #define CK_T2_SCR(A, I) do { A ^= A >> 47; A ^= sec[16 + I]; A *= CK_P32_1; } while (0)
-                        CK_T2_SCR(acc0, 0); CK_T2_SCR(acc1, 1); CK_T2_SCR(acc2, 2); CK_T2_SCR(acc3, 3);
-                        CK_T2_SCR(acc4, 4); CK_T2_SCR(acc5, 5); CK_T2_SCR(acc6, 6); CK_T2_SCR(acc7, 7);
-#undef CK_T2_SCR
-                    }
-                }
-                if (want_out) {
-                    uint4 d[4];
-#pragma unroll
-                    for (u32 i = 0; i < 4; i++) d[i] = lds128(dsc + 16u * (8u * i + (lane >> 2)));   // records 8 i + (lane >> 2)
-                    sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);
-                    __syncwarp();
-                    const u32 c = 4 * s + (lane & 3u);
-                    uint4 g[4];
-#pragma unroll
-                    for (u32 i = 0; i < 4; i++) g[i] = lds128(ord + 640u * i);                       // piece lane & 3
-#pragma unroll
-                    for (u32 i = 0; i < 4; i++)
-                        if (c < d[i].z) *reinterpret_cast<uint4 *>(((u64)d[i].y << 32 | d[i].x) + 64ull * s + 16u * (lane & 3u)) = g[i];
-                    __syncwarp();
+#define CK_S2_ROUND(XA, XB, xa, xs, YA, YB, ya, ys)                                                                 \
+            {                                                                                                       \
+                uint4 v[4];                                                                                         \
+                {                                                                                                   \
+                    u32 W[4];                                                                                       \
+                    CK_S2_WINDOWS(W, XA, XB, xa, xs);                                                               \
+                    if (s + 1 < rounds) {                                                                           \
+                        CK_S2_FETCH(YA, YB, ya, ys);                                                                \
+                        const int pa = B + 3 * step;           /* four rounds ahead, inside the record only */      \
+                        if ((u32)pa < nn) prefetch_l2(base + (((u32)pa >> 6) << 4));                                \
+                    }                                                                                               \
+                    _Pragma("unroll") for (int k = 0; k < 4; k++) v[k] = t2_ascii16(__funnelshift_l(W[k], W[k], rot), T, sa, sb); \
+                }                                                                                                   \
+                if (want_hash && s < nfull) {                                                                       \
+                    const u32 ks = s & 15u;                                                                         \
+                    t2_acc16(acc0, acc1, v[0], sec[ks + 0], sec[ks + 1]);                                           \
+                    t2_acc16(acc2, acc3, v[1], sec[ks + 2], sec[ks + 3]);                                           \
+                    t2_acc16(acc4, acc5, v[2], sec[ks + 4], sec[ks + 5]);                                           \
+                    t2_acc16(acc6, acc7, v[3], sec[ks + 6], sec[ks + 7]);                                           \
+                    if (ks == 15u) {       /* a 1024-byte block is complete (s + 1 <= nfull: more input follows) */ \
+                        CK_T2_SCR(acc0, 0); CK_T2_SCR(acc1, 1); CK_T2_SCR(acc2, 2); CK_T2_SCR(acc3, 3);             \
+                        CK_T2_SCR(acc4, 4); CK_T2_SCR(acc5, 5); CK_T2_SCR(acc6, 6); CK_T2_SCR(acc7, 7);             \
+                    }                                                                                               \
+                }                                                                                                   \
+                if (want_out) {                                                                                     \
+                    sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);      \
+                    __syncwarp();                                                                                   \
+                    const u32 c = 4 * s + (lane & 3u);                                                              \
+                    uint4 g[4], d[4];                                                                               \
+                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) {    /* records 8 i + (lane >> 2), piece lane & 3 */ \
+                        g[i] = lds128(ord + 640u * i);                                                              \
+                        d[i] = lds128(dsc + 16u * (8u * i + (lane >> 2)));                                          \
+                    }                                                                                               \
+                    _Pragma("unroll") for (u32 i = 0; i < 4; i++)                                                   \
+                        if (c < d[i].z) *reinterpret_cast<uint4 *>(((u64)d[i].y << 32 | d[i].x) + 64ull * s + 16u * (lane & 3u)) = g[i]; \
+                    __syncwarp();                                                                                   \
+                }                                                                                                   \
+                if (++s >= rounds) break;                                                                           \
+            }
+            if (rounds) {
+                CK_S2_FETCH(XA0, XB0, xa0, xs0);
+                u32 s = 0;
+#pragma unroll 1
+                for (;;) {
+                    CK_S2_ROUND(XA0, XB0, xa0, xs0, XA1, XB1, xa1, xs1)
+                    CK_S2_ROUND(XA1, XB1, xa1, xs1, XA0, XB0, xa0, xs0)
                 }
             }
             if (want_hash) {
                 // last stripe: canonical bytes [n - 64, n) = the four chunks that end where chunk 0 starts
                 B = strand ? p0 + 16 : p0 - 64;
                 if ((u32)B >= nn) B += nstep;
-                CK_S2_FETCH();
+                CK_S2_FETCH(XA0, XB0, xa0, xs0);
                 u32 W[4];
-                CK_S2_WINDOWS(W);
+                CK_S2_WINDOWS(W, XA0, XB0, xa0, xs0);
                 {
                     const uint4 v0 = t2_ascii16(__funnelshift_l(W[0], W[0], rot), T, sa, sb);
                     t2_acc16(acc0, acc1, v0, c_lastsec[0], c_lastsec[1]);
@@ -325,6 +352,8 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 3) k_canon_s2(CanonArgs a)
             }
 #undef CK_S2_FETCH
 #undef CK_S2_WINDOWS
+#undef CK_S2_ROUND
+#undef CK_T2_SCR
         }
         if (fast) {
             const u32 start = os >> 1, strand = os & 1u;
