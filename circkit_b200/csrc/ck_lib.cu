@@ -360,7 +360,8 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records);
     ctx->launches += 2;
     CanonIO io{};
-    io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = s.d_len; io.lane = s.d_lane;
+    // without normalisation every byte is a symbol: lengths are the offset differences and the lane-per-record kernel applies
+    io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = (flags & CK_F_NORMALIZE) ? s.d_len : nullptr; io.lane = s.d_lane;
     io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;

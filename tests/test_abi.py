@@ -62,3 +62,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("ck_oracle_free", ""), f"{f} mentions the oracle"
+
+
+def test_class_masks_match_the_header():
+    """device.class_mask_for / CLASS_NAMES agree with the CK_CLASS_* promise bits of include/circkit_b200.h."""
+    import re
+    from circkit_b200 import device as D
+    hdr = open(os.path.join(ROOT, "include", "circkit_b200.h")).read()
+    bits = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define CK_CLASS_(\w+) \(1u << (\d+)\)", hdr)}
+    assert len(bits) == 6
+    for name, bit in bits.items():
+        assert D.CLASS_NAMES[bit] == name.replace("2bit", "2bit"), (name, bit)
+    assert D.class_mask_for(250, 400) == 1 << 0
+    assert D.class_mask_for(200, 5000) == (1 << 0) | (1 << 1) | (1 << 10) | (1 << 11)
+    assert D.class_mask_for(5000, 200000) == (1 << 11) | (1 << 2) | (1 << 3)
+    assert D.class_mask_for(513, 513) == 1 << 1

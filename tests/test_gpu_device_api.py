@@ -69,6 +69,54 @@ def test_device_path_matches_oracle(env, name, kind, lo, hi, dup, adv, mask, n, 
         assert (wfirst != np.arange(n)).sum() > 0.5 * n * dup / 1000     # duplicates were really injected and found
 
 
+@pytest.mark.parametrize("want_bytes,want_hash", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("lo,hi,mask_extra", [(250, 400, 0), (100, 700, 0), (3000, 8192, 0), (250, 400, 1 << 1)])
+def test_lane_kernel_variants(env, want_bytes, want_hash, lo, hi, mask_extra):
+    """Every compile-time variant of the lane-per-record kernel (hash? bytes? work list?), in direct mode (one
+    class promised), through the sorted work list (several classes), with records it must leave to the retry
+    kernels (n < 128, n <= 240 with a hash) and with XXH3 block scrambles (n > 1024)."""
+    ctx, D, torch = env
+    n = 6000 if hi <= 1000 else 1500
+    b = D.synth_batch(ctx, seed=23, first_index=0, n_records=n, kind=0, lo=lo, hi=hi, dup_permille=100)
+    outs = D.CanonOutputs(n, b.total, b.offsets.device, want_bytes=want_bytes, want_hash=want_hash, aligned=True)
+    ws = D.Workspace(ctx, n)
+    D.canon_packed2(ctx, b, outs, ws, class_mask=D.class_mask_for(lo, hi) | mask_extra)
+    D.check(ctx, ws)
+    ascii_, off, want = _oracle_for(ctx, D, torch, b, n)
+    assert np.array_equal(outs.start[:n].cpu().numpy().astype(np.uint32), want["start"])
+    assert np.array_equal(outs.strand[:n].cpu().numpy(), want["strand"])
+    if want_hash:
+        assert np.array_equal(outs.hash[:n].cpu().numpy().astype(np.uint64), want["hash"])
+    if want_bytes:
+        arena = outs.out.cpu().numpy()
+        starts = ctx.aligned_starts(off).astype(np.int64)
+        lens = (off[1:] - off[:-1]).astype(np.int64)
+        src = np.repeat(starts - off[:-1].astype(np.int64), lens) + np.arange(int(off[-1]), dtype=np.int64)
+        assert np.array_equal(arena[src], want["out"])
+
+
+def test_packed_arena_carries_its_circular_extension(env):
+    """Format of the packed arena (ck_device.cuh): record i at 16-byte granule (offsets[i] >> 6) + 2 i, units
+    0 .. (n >> 4) + 4 hold S[b mod n]."""
+    ctx, D, torch = env
+    n = 300
+    b = D.synth_batch(ctx, seed=5, first_index=0, n_records=n, kind=0, lo=1, hi=700)
+    ascii_ = D.unpack_ascii(ctx, b, n).cpu().numpy()
+    off = b.offsets.cpu().numpy().astype(np.int64)
+    words = b.packed2.cpu().numpy().view(np.uint32)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    for i in list(range(40)) + [n - 1]:
+        L = int(off[i + 1] - off[i])
+        g = (int(off[i]) >> 6) + 2 * i
+        units = words[4 * g: 4 * g + (L >> 4) + 5]
+        seq = [code[int(c)] for c in ascii_[off[i]: off[i + 1]]]
+        for j, u in enumerate(units):
+            want = 0
+            for k in range(16):
+                want = (want << 2) | seq[(16 * j + k) % L]
+            assert int(u) == want, (i, L, j)
+
+
 def test_class_promise_violation_is_reported(env):
     import circkit_b200
     ctx, D, torch = env
