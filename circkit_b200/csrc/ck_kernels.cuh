@@ -287,37 +287,49 @@ struct ClassifyArgs {
 };
 __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    int cls = -1;
-    u32 n = 0;
-    if (i < a.n_records) {
-        n = a.lens ? a.lens[i] : (u32)(a.offsets[i + 1] - a.offsets[i]);
-        const u32 bits = a.lane ? a.lane[i] : 2u;
-        if (n == 0) cls = CLS_EMPTY;
-        else if (bits == 2) cls = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M
-                                : n <= cls_max_n(CLS_W2L) ? CLS_W2L : n <= cls_max_n(CLS_W2X) ? CLS_W2X
-                                : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
-        else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
-        else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
+    __shared__ u32 cnt[16];                                    // per-CTA class counts: one global atomic per class and CTA
+    if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 nthreads = gridDim.x * blockDim.x;
+    const u32 rounds = (a.n_records + nthreads - 1) / nthreads;
+    for (u32 r = 0; r < rounds; r++) {
+        const u32 i = r * nthreads + blockIdx.x * blockDim.x + threadIdx.x;
+        int cls = -1;
+        u32 n = 0;
+        if (i < a.n_records) {
+            n = a.lens ? a.lens[i] : (u32)(a.offsets[i + 1] - a.offsets[i]);
+            const u32 bits = a.lane ? a.lane[i] : 2u;
+            if (n == 0) cls = CLS_EMPTY;
+            else if (bits == 2) cls = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M
+                                    : n <= cls_max_n(CLS_W2L) ? CLS_W2L : n <= cls_max_n(CLS_W2X) ? CLS_W2X
+                                    : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
+            else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
+            else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
+        }
+        if (a.direct_mask) {
+            const u32 m = __ballot_sync(CK_FULL, cls >= 0 && !((a.direct_mask >> cls) & 1u));
+            if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(cnt + CLS_HUGE, __popc(m));
+            continue;
+        }
+        if (cls >= 0) {
+            // key = (rank of the class in list order) : (length on a 1/4-octave log scale: lanes of a warp differ by < 19 % in
+            // length, and a bin is dense enough that its consecutive members sit close together in the arenas; measured on
+            // config 2: 1/32 octave 9.7 ms, 1/8 octave 8.6 ms, 1/4 octave 8.4 ms)
+            const u32 msb = 31u - __clz(n | 1u);
+            const u32 bin = (msb << 5) | ((((n << (31u - msb)) >> 29) & 3u) << 3);
+            a.keys[i] = (cls_rank(cls) << 10) | bin; a.vals[i] = i;
+        }
+        // warp-aggregated counting: one shared-memory atomic per (warp, class present)
+        u32 todo = __ballot_sync(CK_FULL, cls >= 0);
+        while (todo) {
+            const int c = __shfl_sync(CK_FULL, cls, __ffs(todo) - 1);
+            const u32 m = __ballot_sync(CK_FULL, cls == c);
+            if (lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(cnt + c, __popc(m));
+            todo &= ~m;
+        }
     }
-    if (a.direct_mask) {
-        const u32 m = __ballot_sync(CK_FULL, cls >= 0 && !((a.direct_mask >> cls) & 1u));
-        if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + CLS_HUGE, __popc(m));
-        return;
-    }
-    if (cls >= 0) {
-        // key = (rank of the class in list order) : (length on a 1/4-octave log scale: lanes of a warp differ by < 19 % in
-        // length, and a bin is dense enough that its consecutive members sit close together in the arenas; measured on
-        // config 2: 1/32 octave 9.7 ms, 1/8 octave 8.6 ms, 1/4 octave 8.4 ms)
-        const u32 msb = 31u - __clz(n | 1u);
-        const u32 bin = (msb << 5) | ((((n << (31u - msb)) >> 29) & 3u) << 3);
-        a.keys[i] = (cls_rank(cls) << 10) | bin; a.vals[i] = i;
-    }
-    // warp-aggregated counting, one atomic per (warp, class present)
-    for (int c = 0; c < CLS_COUNT; c++) {
-        const u32 m = __ballot_sync(CK_FULL, cls == c);
-        if (m && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(a.counts + c, __popc(m));
-    }
+    __syncthreads();
+    if (threadIdx.x < 16 && cnt[threadIdx.x]) atomicAdd(a.counts + threadIdx.x, cnt[threadIdx.x]);
 }
 // run starts of the sorted index list (classes in cls_rank order).  Layout of the 64 counters:
 //   [0, 12)  records per class        [12]  records of the lane-kernel classes together (one launch)

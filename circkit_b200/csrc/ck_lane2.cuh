@@ -8,6 +8,8 @@ namespace ck {
 
 __constant__ u64 c_lastsec[8];      // LE u64 of the secret at byte offsets 121 + 8 i (XXH3 last stripe)
 __constant__ u64 c_mergesec[8];     // LE u64 of the secret at byte offsets 11 + 8 i  (XXH3 merge)
+__constant__ u64 c_midsec[16];      // LE u64 of the secret at byte offsets 3 + 8 i   (XXH3 129..240: rounds 8.., start offset 3);
+                                    // [14], [15]: offsets 119, 127 (the last 16 bytes: 136 - 17)
 
 __device__ __forceinline__ uint4 lds128(u32 a)
 {

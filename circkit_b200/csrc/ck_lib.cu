@@ -1,5 +1,6 @@
 // ck_lib.cu -- C ABI (include/circkit_b200.h) over the kernels in ck_kernels.cuh.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -226,7 +227,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     u32 *k0 = io.lists, *k1 = k0 + stride, *v0 = k1 + stride, *v1 = v0 + stride;
     if (io.lists_bytes < 16 * stride) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
     ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u};
-    k_classify<<<(io.n + 255) / 256, 256, 0, st>>>(ca);
+    k_classify<<<std::min<u32>((io.n + 255) / 256, 16u * (u32)ctx->num_sms), 256, 0, st>>>(ca);
     ctx->launches++;
     const u32 *sorted = nullptr;
     u32 *retry = v0;                                           // direct mode: the sort buffers are free
@@ -437,10 +438,13 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     CK_INIT(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
     CK_INIT(cudaMemcpyToSymbol(c_secret, secret, sizeof(secret)));
     {
-        u64 last[8], merge[8];
+        u64 last[8], merge[8], mid[16];
         for (int i = 0; i < 8; i++) { memcpy(&last[i], secret + 121 + 8 * i, 8); memcpy(&merge[i], secret + 11 + 8 * i, 8); }
+        for (int i = 0; i < 14; i++) memcpy(&mid[i], secret + 3 + 8 * i, 8);
+        memcpy(&mid[14], secret + 119, 8); memcpy(&mid[15], secret + 127, 8);
         CK_INIT(cudaMemcpyToSymbol(c_lastsec, last, sizeof(last)));
         CK_INIT(cudaMemcpyToSymbol(c_mergesec, merge, sizeof(merge)));
+        CK_INIT(cudaMemcpyToSymbol(c_midsec, mid, sizeof(mid)));
     }
     if (alloc_scratch(ctx, ctx->dev_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
     const u64 B = cfg->max_batch_bytes, R = cfg->max_batch_records;

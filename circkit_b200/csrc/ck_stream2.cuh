@@ -23,8 +23,8 @@
 //                 units already in flight;
 //   * write     : a round's 64 bytes per lane go through a padded shared-memory stage (the kernel's only shared
 //                 memory) and leave as 128-bit stores in which four consecutive lanes cover 64 contiguous bytes;
-//   * retry     : records a lane cannot finish alone (equal minimal 8-mers, n < 128, the short XXH3 forms of
-//                 n <= 240) are appended to a retry list that the warp- / CTA-per-record kernels work off afterwards.
+//   * retry     : records a lane cannot finish alone (equal minimal 8-mers, n < 128, n = 128 when a hash is wanted)
+//                 are appended to a retry list that the warp- / CTA-per-record kernels work off afterwards.
 // Work lists come sorted by (class, length) (k_classify + radix sort), so the lanes of a warp run the same trip counts.
 #pragma once
 #include "ck_lane2.cuh"
@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
             fetch_head(((u64)oe.y << 32) | oe.x, oe.z - oe.x, rec1);
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
-        // lane-private fast path: n >= 128 (and the long XXH3 form when a hash is wanted)
-        bool fast = in_class && n >= (want_hash ? 241u : 128u);
+        // lane-private fast path: n >= 128 (with a hash: n >= 129, the 129..240 and the long XXH3 forms)
+        bool fast = in_class && n >= (want_hash ? 129u : 128u);
         const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 4 are valid
         u8 *dst = want_out ? a.out + 16ull * ((off >> 4) + rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
@@ -245,6 +245,10 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
             const u32 rounds = __reduce_max_sync(CK_FULL, (nchunks + 3) >> 2);
             u64 acc0 = CK_P32_3, acc1 = CK_P64_1, acc2 = CK_P64_2, acc3 = CK_P64_3;
             u64 acc4 = CK_P64_4, acc5 = CK_P32_2, acc6 = CK_P64_5, acc7 = CK_P32_1;
+            // XXH3 129..240 form: one 16-byte mix per chunk instead of stripes (work lists group such records in their own warps)
+            const u32 nbr = (want_hash && fast && nn <= 240u) ? nn >> 4 : 0u;    // rounds of 16 bytes
+            const bool any_mid = want_hash && __any_sync(CK_FULL, nbr != 0);
+            u64 mida = 0, midb = 0;
             // (destination, chunks) of every record of the batch, read back by the lanes that carry its bytes out of the stage
             const u32 dsc = aux + CK_T2_AUX_BYTES + 1024u + 384u;
             if (want_out) {
@@ -302,6 +306,14 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                         CK_T2_SCR(acc4, 4); CK_T2_SCR(acc5, 5); CK_T2_SCR(acc6, 6); CK_T2_SCR(acc7, 7);             \
                     }                                                                                               \
                 }                                                                                                   \
+                if (any_mid) {                                                                                      \
+                    _Pragma("unroll") for (u32 k = 0; k < 4; k++) {                                                 \
+                        const u32 i = 4 * s + k;                                                                    \
+                        const u64 lo = ((u64)v[k].y << 32) | v[k].x, hi = ((u64)v[k].w << 32) | v[k].z;             \
+                        if (i < 8) { const u64 t = mul128_fold64(lo ^ sec[2 * i], hi ^ sec[2 * i + 1]); if (i < nbr) mida += t; }      \
+                        else if (i < 15) { const u64 t = mul128_fold64(lo ^ c_midsec[2 * i - 16], hi ^ c_midsec[2 * i - 15]); if (i < nbr) midb += t; } \
+                    }                                                                                               \
+                }                                                                                                   \
                 if (want_out) {                                                                                     \
                     sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);      \
                     __syncwarp();                                                                                   \
@@ -349,6 +361,17 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                 r += mul128_fold64(acc4 ^ c_mergesec[4], acc5 ^ c_mergesec[5]);
                 r += mul128_fold64(acc6 ^ c_mergesec[6], acc7 ^ c_mergesec[7]);
                 h = xxh3_avalanche(r);
+            }
+            if (any_mid) {
+                // the last 16 canonical bytes [n - 16, n): the chunk that ends where chunk 0 starts
+                int q = strand ? p0 + 16 : p0 - 16;
+                if ((u32)q >= nn) q += nstep;
+                const u8 *ad = base + (((u32)q >> 4) << 2);
+                const u32 w = __funnelshift_l(ldg32(ad + 4), ldg32(ad), 2u * (u32)q);
+                const uint4 vv = t2_ascii16(__funnelshift_l(w, w, rot), T, sa, sb);
+                const u64 lo = ((u64)vv.y << 32) | vv.x, hi = ((u64)vv.w << 32) | vv.z;
+                const u64 tail = mul128_fold64(lo ^ c_midsec[14], hi ^ c_midsec[15]);
+                if (nbr) h = xxh3_avalanche(xxh3_avalanche((u64)nn * CK_P64_1 + mida) + midb + tail);
             }
 #undef CK_S2_FETCH
 #undef CK_S2_WINDOWS
