@@ -212,6 +212,7 @@ def main():
         table = D.DeviceTable(ctx, capacity_keys=int(R * 1.05) + 1024, dev=dev)   # owns ~R keys of the global set
         first = torch.empty(R, dtype=torch.int64, device=dev)
         slot_cache = {}
+        partitioner = D.OwnerPartitioner(ctx, R, world, dev) if world > 1 else None
 
         def first_fn(h, idx):
             m = h.numel()
@@ -220,7 +221,7 @@ def main():
                 slot_cache[key] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
                                    torch.empty(max(m, 1), dtype=torch.int64, device=dev))
             slots, out = slot_cache[key]
-            table.insert(h, m, slots, index=idx)
+            table.insert(h, m, slots, index=idx, base_index=base_index if idx is None else 0)
             table.first(slots, m, out)
             return out[:m]
 
@@ -228,7 +229,7 @@ def main():
         D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
         if w["uniq"]:
             table.clear()
-            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn)
+            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn, partition_fn=partitioner)
             first.copy_(f)
 
     def sync_all():

@@ -433,4 +433,51 @@ __global__ void k_table_clear(TableSlot *slots, u64 n, u64 *side_first)
     if (blockIdx.x == 0 && threadIdx.x == 0) *side_first = ~0ULL;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hash-range partition for multi-GPU uniq: owner = floor(hash * world / 2^64).  Two passes over
+// the local hashes: counts per owner, then a scatter of (hash, global index) into per-owner runs of the send
+// buffers (order inside a run is free: the owner keeps the minimum index per key).  pos[i] = where record i went, so
+// the answer that comes back in send-buffer order can be gathered back into input order.
+struct OwnerArgs {
+    const u64 *hash; u32 n; u32 world; u64 base_index;
+    u32 *counts;       // [world] records per owner, then [world] scatter cursors (both zeroed by the caller)
+    u64 *send_hash, *send_index; u32 *pos;
+};
+// floor(hash * world / 2^64) on the top 32 bits.  Written with __umulhi: nvcc 12.9 turned the 64-bit form
+// (((h >> 32) * world) >> 32), used as a shared-memory index, into a low multiply (every record went to owner 0).
+__device__ __forceinline__ u32 owner_of_hash(u64 h, u32 world) { return __umulhi((u32)(h >> 32), world); }
+__global__ void __launch_bounds__(256) k_owner_count(OwnerArgs a)
+{
+    __shared__ u32 cnt[32];
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x)
+        atomicAdd(cnt + owner_of_hash(a.hash[i], a.world), 1u);
+    __syncthreads();
+    if (threadIdx.x < a.world && cnt[threadIdx.x]) atomicAdd(a.counts + threadIdx.x, cnt[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_owner_scatter(OwnerArgs a)
+{
+    __shared__ u32 cnt[32], basep[32];
+    const u32 per = (a.n + gridDim.x - 1) / gridDim.x;         // this CTA's contiguous slice
+    const u32 lo = min(a.n, blockIdx.x * per), hi = min(a.n, lo + per);
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(cnt + owner_of_hash(a.hash[i], a.world), 1u);
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        u32 start = 0;                                         // run start of this owner = counts of the owners below it
+        for (u32 o = 0; o < threadIdx.x; o++) start += a.counts[o];
+        basep[threadIdx.x] = start + atomicAdd(a.counts + a.world + threadIdx.x, cnt[threadIdx.x]);
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const u64 h = a.hash[i];
+        const u32 o = owner_of_hash(h, a.world);
+        const u32 p = basep[o] + atomicAdd(cnt + o, 1u);
+        a.send_hash[p] = h; a.send_index[p] = a.base_index + i; a.pos[i] = p;
+    }
+}
+
 }  // namespace ck

@@ -719,6 +719,24 @@ int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_by
     if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
     return table_first(ctx, (cudaStream_t)stream, slots, nslots, side, U(slot_scratch), n, U(out_first_index));
 }
+int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, uint32_t world,
+                           uint64_t *send_hash, uint64_t *send_index, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host)
+{
+    if (!ctx || !hash64 || !send_hash || !send_index || !pos || !counts_dev || !counts_host || world < 1 || world > 32)
+        return ctx ? fail(ctx, CK_ERR_ARG, "bad partition arguments") : CK_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, 2 * world * sizeof(u32), st));
+    OwnerArgs a{U(hash64), n, world, base_index, counts_dev, U(send_hash), U(send_index), pos};
+    if (n) {
+        const u32 grid = std::min<u32>((n + 255) / 256, 8u * (u32)ctx->num_sms);
+        k_owner_count<<<grid, 256, 0, st>>>(a);
+        k_owner_scatter<<<grid, 256, 0, st>>>(a);
+        ctx->launches += 2;
+    }
+    CK_CUDA(ctx, cudaMemcpyAsync(counts_host, counts_dev, world * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
+    return CK_OK;
+}
 uint64_t ck_launch_count(const ck_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int ck_kernel_timing(ck_ctx *ctx, int enable)

@@ -121,6 +121,28 @@ class DeviceTable:
                                                          _p(slot_scratch), n, _p(out_first)))
 
 
+class OwnerPartitioner:
+    """Buckets local (hash64, global index) pairs by owning rank with two CUDA kernels (the send side of the
+    hash-range exchange, exchange.exchange_first_index)."""
+
+    def __init__(self, ctx: Context, n: int, world: int, dev=None):
+        dev = dev or torch.device("cuda", ctx.device)
+        self.ctx, self.world = ctx, world
+        self.h = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        self.i = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        self.pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.counts_dev = torch.zeros(2 * world, dtype=torch.int32, device=dev)
+        self.counts_host = (C.c_uint32 * world)()
+
+    def __call__(self, hash64: torch.Tensor, base_index: int, world: int):
+        n = hash64.numel()
+        assert world == self.world and n <= self.h.numel()
+        self.ctx._check(self.ctx._lib.ck_dev_owner_partition(self.ctx.handle, _stream(), _p(hash64), n, base_index, world,
+                                                             _p(self.h), _p(self.i), _p(self.pos), _p(self.counts_dev),
+                                                             self.counts_host))
+        return self.h[:n], self.i[:n], self.pos[:n], [int(c) for c in self.counts_host]
+
+
 def kernel_times(ctx: Context):
     """{class name: (total ms, launches)} since the last call (needs ck_kernel_timing(1))."""
     n = len(CLASS_NAMES)

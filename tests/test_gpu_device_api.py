@@ -168,3 +168,26 @@ def test_full_size_properties_config1(env):
     table.first(slots, n, first)
     uniq = int((first == torch.arange(n, device=first.device)).sum().item())
     assert abs(uniq - 0.7 * n) < 0.01 * n            # ~30 % injected duplicates, all found, nothing else merged
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_owner_partition_matches_owner_of(env, world):
+    """ck_dev_owner_partition (send side of the hash-range exchange) against exchange.owner_of: every pair lands
+    in its owner's run, runs are contiguous in owner order, pos maps records to their slot."""
+    ctx, D, torch = env
+    from circkit_b200.exchange import owner_of
+    n, base = 200_003, 7_000_000_000
+    g = torch.Generator(device="cuda").manual_seed(world)
+    h = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    h[:4] = torch.tensor([0, -1, 2**63 - 1, -2**63], dtype=torch.int64)
+    part = D.OwnerPartitioner(ctx, n, world)
+    hs, is_, pos, counts = part(h, base, world)
+    own = owner_of(h, world)
+    assert counts == torch.bincount(own, minlength=world).tolist()
+    assert torch.equal(hs[pos.long()], h)
+    assert torch.equal(is_[pos.long()], torch.arange(base, base + n, device="cuda"))
+    assert torch.equal(torch.sort(pos.long()).values, torch.arange(n, device="cuda"))
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    o_sorted = owner_of(hs, world).cpu().numpy()
+    for r in range(world):
+        assert (o_sorted[starts[r]: starts[r + 1]] == r).all()
