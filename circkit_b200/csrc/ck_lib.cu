@@ -244,9 +244,9 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         k_list_starts<<<1, 32, 0, st>>>(io.counts);
         ctx->launches += 2;
     }
-    // specialised variants for the resident fast path (packed lengths, both strands, aligned bytes or none): the
-    // lane-per-record streaming kernel; everything else: the run-time-option warp-per-record kernel
-    const bool fastv = io.packed2 && !io.lens && !(io.mode & 1u) && (!io.out || (io.mode & 2u)) && io.out_start && io.out_strand;
+    // both strands, aligned bytes or none: the lane-per-record streaming kernel; everything else (forward-only library
+    // calls, output at the input's offsets): the run-time-option warp-per-record kernel
+    const bool fastv = io.packed2 && !(io.mode & 1u) && (!io.out || (io.mode & 2u)) && io.out_start && io.out_strand;
     const u32 lane_classes = (1u << CLS_W2S) | (1u << CLS_W2M) | (1u << CLS_W2L) | (1u << CLS_W2X);
     auto timed = [&](int slot, cudaEvent_t &e0, cudaEvent_t &e1, bool begin) -> cudaError_t {
         if (!ctx->timing) return cudaSuccess;

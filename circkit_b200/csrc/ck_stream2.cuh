@@ -80,10 +80,14 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         if (bytes > 192) prefetch_l2(nb + 192);
     };
 
+    // (offset, end) of a record, or (offset, normalised length) when the batch carries lengths of its own
+    const bool has_lens = a.lens != nullptr;
     auto fetch_offsets = [&](u32 rec, u32 slot) {
         cp_async8(offs + 512u * slot, a.offsets + rec);
-        cp_async8(offs + 512u * slot + 8u, a.offsets + rec + 1);
+        if (has_lens) cp_async4(offs + 512u * slot + 8u, a.lens + rec);
+        else cp_async8(offs + 512u * slot + 8u, a.offsets + rec + 1);
     };
+    auto length_of = [&](const uint4 &oe) { return has_lens ? oe.z : oe.z - oe.x; };
     // ---- prologue: offsets of batches 0 and 1, (work lists) record indices of batches 0..2
     u32 rq = 0;                                                    // work lists: record index two batches ahead
     {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         __syncwarp();
         if (i0 < count) {
             const uint4 oe = lds128(offs);
-            fetch_head(((u64)oe.y << 32) | oe.x, oe.z - oe.x, r0);
+            fetch_head(((u64)oe.y << 32) | oe.x, length_of(oe), r0);
         }
     }
     u32 kb = 0;                                                    // batch counter of this warp
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         {
             const uint4 oe = lds128(offs + 512u * sl);
             if (use_list) rec = lds32(recs + 128u * (kb % 3u));
-            if (have) { off = ((u64)oe.y << 32) | oe.x; n = oe.z - oe.x; } else rec = 0;
+            if (have) { off = ((u64)oe.y << 32) | oe.x; n = length_of(oe); } else rec = 0;
             const u32 idx2 = idx + 2 * bstride;
             if (idx2 < count) fetch_offsets(use_list ? rq : idx2, sl);
             if (use_list) {
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         if (idx + bstride < count) {
             const uint4 oe = lds128(offs + 512u * (sl ^ 1u));
             const u32 rec1 = use_list ? lds32(recs + 128u * ((kb + 1u) % 3u)) : idx + bstride;
-            fetch_head(((u64)oe.y << 32) | oe.x, oe.z - oe.x, rec1);
+            fetch_head(((u64)oe.y << 32) | oe.x, length_of(oe), rec1);
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         // lane-private fast path: n >= 128 (with a hash: n >= 129, the 129..240 and the long XXH3 forms)
