@@ -88,14 +88,14 @@ class Context:
 
     # -- batch API (host buffers)
     def out_arena_bytes(self, total: int, n: int) -> int:
-        """Size of the CK_F_ALIGNED_OUT output arena (record i at 16 * ((offsets[i] >> 4) + i))."""
+        """Size of the CK_F_ALIGNED_OUT output arena (record i at 32 * ((offsets[i] >> 5) + i))."""
         return int(self._lib.ck_out_arena_bytes(total, n))
 
     @staticmethod
     def aligned_starts(offsets: np.ndarray) -> np.ndarray:
         """Byte position of every record in the aligned output arena."""
         off = np.asarray(offsets[:-1], dtype=np.uint64)
-        return 16 * ((off >> np.uint64(4)) + np.arange(len(off), dtype=np.uint64))
+        return 32 * ((off >> np.uint64(5)) + np.arange(len(off), dtype=np.uint64))
 
     def canon_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool, no_bytes=False,
                      aligned=False):
@@ -116,7 +116,7 @@ class Context:
     def canonicalize_batch(self, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, want_bytes=True,
                            aligned=False):
         """Worker closure over a batch (src/canonicalize.rs:21-30): returns dict(out, lens, start, strand, hash).
-        aligned=True: `out` is the 16-byte-aligned arena (record i at aligned_starts(offsets)[i])."""
+        aligned=True: `out` is the 32-byte-aligned arena (record i at aligned_starts(offsets)[i])."""
         arena = np.ascontiguousarray(arena, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self.canon_submit(0, arena, offsets, normalize=normalize, no_bytes=not want_bytes, aligned=aligned)

@@ -41,6 +41,11 @@ __constant__ Tables c_tab;   // single translation unit (ck_lib.cu): defined her
 // (k_extend_packed2): a 16-base window that starts anywhere in the record never needs wrap logic.
 __host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec) { return 2 * ((off >> 6) + 2 * rec); }     // u64 word index
 __host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records) { return 2 * ((total >> 6) + 2 * n_records + 2); }
+// aligned output arena (CK_F_ALIGNED_OUT): record i's canonical bytes start at byte 32 * ((offsets[i] >> 5) + i).  32 bytes =
+// one DRAM / L2 sector: a 64-byte output round of the lane kernel then covers whole sectors only (with 16-byte alignment half
+// of the records wrote half sectors at both ends of every round, which the memory system pays for with fill reads).
+__host__ __device__ __forceinline__ u64 out_byte(u64 off, u64 rec) { return 32 * ((off >> 5) + rec); }
+__host__ __device__ __forceinline__ u64 out_bytes_total(u64 total, u64 n_records) { return 32 * ((total >> 5) + n_records) + 32; }
 
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }

@@ -71,7 +71,7 @@ struct CanonArgs {
     u32 smem_units;         // u32 units reserved per strand in (shared) staging memory
     u32 *xglobal;           // CLS_HUGE only: strands staged here, 2 * smem_units u32 per CTA
     u32 mode;               // bit0: forward strand only (lmsr / lmsr_index, lib/src/canonicalize.rs:5,41)
-                            // bit1: aligned output arena: record i's bytes start at 16 * ((offsets[i] >> 4) + i)
+                            // bit1: aligned output arena: record i's bytes start at out_byte(offsets[i], i)
     u32 min_n, max_n;       // length range of this launch's class (checked when there is no list)
     u32 *retry;             // lane-per-record kernel: records it leaves to the warp / CTA kernels, appended per class at
     u32 *retry_counts;      // retry[retry_counts[16 + class] + atomicAdd(retry_counts + class, 1)]
@@ -136,7 +136,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
     stage_record<BITS, G>(in, Xf, Xr);
     RecordOut o = canonical_start<BITS, G>(Xf, Xr, n, scr, red, (a.mode & 1u) != 0);
     const u32 *X = o.strand ? Xr : Xf;
-    if (a.out) emit_ascii<BITS, G>(X, n, o.start, a.out + ((a.mode & 2u) ? 16ull * ((off >> 4) + rec) : off));
+    if (a.out) emit_ascii<BITS, G>(X, n, o.start, a.out + ((a.mode & 2u) ? out_byte(off, rec) : off));
     u64 h = 0;
     if (a.out_hash) h = xxh3_canonical<BITS, G>(X, n, o.start, hbuf, red);
     if (G::rank() == 0) {

@@ -455,7 +455,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaEventCreateWithFlags(&s.inserted, cudaEventDisableTiming));
             CK_INIT(cudaMalloc(&s.d_raw, B + 16));
             CK_INIT(cudaMalloc(&s.d_norm, B + 16));
-            CK_INIT(cudaMalloc(&s.d_out, B + 16 * R + 64));
+            CK_INIT(cudaMalloc(&s.d_out, out_bytes_total(B, R) + 64));
             CK_INIT(cudaMalloc(&s.d_p2, p2_words(B, R) * 8));
             CK_INIT(cudaMalloc(&s.d_off, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_len, (R + 1) * 4));
@@ -633,7 +633,7 @@ uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
     if (total_bytes) b += p2_words(total_bytes, n_records) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
     return (b + 255) & ~255ull;
 }
-uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records) { return 16ull * ((total_bytes >> 4) + n_records) + 16; }
+uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records) { return out_bytes_total(total_bytes, n_records); }
 
 int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records,
                          uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand,

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         // lane-private fast path: n >= 128 (with a hash: n >= 129, the 129..240 and the long XXH3 forms)
         bool fast = in_class && n >= (want_hash ? 129u : 128u);
         const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 4 are valid
-        u8 *dst = want_out ? a.out + 16ull * ((off >> 4) + rec) : nullptr;
+        u8 *dst = want_out ? a.out + out_byte(off, rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
         u64 h = 0;
         const u32 nn = fast ? n : 128u;                            // lanes without a fast record walk a dummy geometry

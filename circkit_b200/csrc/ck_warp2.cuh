@@ -13,7 +13,7 @@
 //     per lane, comparing full 16-mers; a unique minimal 16-mer ends the search, anything else takes the duel path;
 //   * ASCII: 16 bases -> 16 letters with 13 ALU ops (two masks split the window into PRMT selector nibbles, four
 //     PRMT look-ups in the register constant "ACGT", four PRMT interleaves), no shared-memory table;
-//   * output: with CK_F_ALIGNED_OUT record i's canonical bytes start at 16 * ((offsets[i] >> 4) + i), so every
+//   * output: with CK_F_ALIGNED_OUT record i's canonical bytes start at 32 * ((offsets[i] >> 5) + i), so every
 //     store is a full 128-bit line piece and the XXH3 stripes read the very same registers (one ASCII
 //     generation feeds both);
 //   * XXH3-64 (n > 240): lane = (stripe, accumulator pair); the last stripe rides in spare lanes of the
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
         }
         const bool in_range = use_list || (n >= a.min_n && n <= a.max_n);    // direct mode: k_classify reported the rest
         const u64 *src = a.packed2 + p2_word(off, rec);
-        u8 *dst = want_out ? a.out + (aligned_out ? 16ull * ((off >> 4) + rec) : off) : nullptr;
+        u8 *dst = want_out ? a.out + (aligned_out ? out_byte(off, rec) : off) : nullptr;
         u32 os = 0;                                               // (start << 1) | strand of the canonical rotation
         u64 h = 0;
         if (!in_range) {

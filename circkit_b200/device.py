@@ -74,7 +74,7 @@ def unpack_ascii(ctx: Context, b: DeviceBatch, n_records: int | None = None) -> 
 class CanonOutputs:
     def __init__(self, n: int, total: int, dev, want_bytes=True, want_hash=True, aligned=False):
         self.aligned = aligned
-        nbytes = 16 * ((total >> 4) + n) + 16 if aligned else max(total, 1) + 16
+        nbytes = 32 * ((total >> 5) + n) + 32 if aligned else max(total, 1) + 16
         self.out = torch.empty(nbytes, dtype=torch.uint8, device=dev) if want_bytes else None
         self.start = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.strand = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)

@@ -45,8 +45,8 @@ extern "C" {
                                src/canonicalize.rs:24-27); without it bytes are used as they are, like
                                circkit::canonicalize (lib/src/canonicalize.rs:54) */
 #define CK_F_NO_BYTES 2u    /* do not produce canonical bytes (start/strand/hash only) */
-#define CK_F_ALIGNED_OUT 4u /* canonical bytes go to a 16-byte-aligned arena: record i starts at byte
-                               16 * ((offsets[i] >> 4) + i) of out_bytes (ck_out_arena_bytes() long) instead of
+#define CK_F_ALIGNED_OUT 4u /* canonical bytes go to a 32-byte-aligned arena: record i starts at byte
+                               32 * ((offsets[i] >> 5) + i) of out_bytes (ck_out_arena_bytes() long) instead of
                                offsets[i].  Every device store is then a full 128-bit store; the host writer reads
                                each record from its aligned start (it copies record by record anyway:
                                src/canonicalize.rs:33-37). */

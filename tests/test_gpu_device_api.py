@@ -45,7 +45,7 @@ def test_device_path_matches_oracle(env, name, kind, lo, hi, dup, adv, mask, n, 
     D.check(ctx, ws)
     ascii_, off, want = _oracle_for(ctx, D, torch, b, n)
     if aligned:
-        # record i lives at 16 * ((offsets[i] >> 4) + i): gather it back to the compact layout
+        # record i lives at 32 * ((offsets[i] >> 5) + i): gather it back to the compact layout
         arena = outs.out.cpu().numpy()
         starts = ctx.aligned_starts(off).astype(np.int64)
         lens = (off[1:] - off[:-1]).astype(np.int64)
