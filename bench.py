@@ -225,11 +225,21 @@ def main():
             table.first(slots, m, out)
             return out[:m]
 
+    def first_pairs_fn(pairs):
+        m = pairs.shape[0]
+        if m not in slot_cache:
+            slot_cache[m] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
+                             torch.empty(max(m, 1), dtype=torch.int64, device=dev))
+        slots, out = slot_cache[m]
+        table.insert_pairs(pairs, m, slots)
+        table.first(slots, m, out)
+        return out[:m]
+
     def step():
         D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
         if w["uniq"]:
             table.clear()
-            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn, partition_fn=partitioner)
+            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn, partition_fn=partitioner, first_pairs_fn=first_pairs_fn)
             first.copy_(f)
 
     def sync_all():
@@ -238,14 +248,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)                     # started before the warm-up: nvidia-smi needs ~100 ms to come up
+    sampler.start()
     for _ in range(args.warmup):
         step()
     sync_all()
     D.check(ctx, ws)
     ctx._lib.ck_kernel_timing(ctx.handle, 1)
     D.kernel_times(ctx)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()

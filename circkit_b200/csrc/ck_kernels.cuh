@@ -392,6 +392,7 @@ struct TableArgs {
     TableSlot *slots; u64 mask;          // capacity - 1 (power of two)
     u64 *side_first;                     // first index of key == EMPTY_KEY
     const u64 *hash; const u64 *index;   // index == null: base_index + i
+    u32 stride;                          // elements between consecutive records in hash / index (2: interleaved pairs)
     u64 base_index; u32 n;
     u64 *slot_of;                        // out: slot found per record (for k_table_first)
     u64 *first_out;                      // out (k_table_first)
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(256) k_table_insert(TableArgs a)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const u64 key = a.hash[i];
-    const u64 idx = a.index ? a.index[i] : a.base_index + i;
+    const u64 key = a.hash[(size_t)i * a.stride];
+    const u64 idx = a.index ? a.index[(size_t)i * a.stride] : a.base_index + i;
     if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); a.slot_of[i] = ~0ULL; return; }
     u64 s = table_home(key, a.mask);
     for (u64 probes = 0; probes <= a.mask; probes++) {
@@ -441,7 +442,7 @@ __global__ void k_table_clear(TableSlot *slots, u64 n, u64 *side_first)
 struct OwnerArgs {
     const u64 *hash; u32 n; u32 world; u64 base_index;
     u32 *counts;       // [world] records per owner, then [world] scatter cursors (both zeroed by the caller)
-    u64 *send_hash, *send_index; u32 *pos;
+    u64 *send_pairs; u32 *pos;   // send buffer: (hash, global index) pairs, 16 bytes per record
 };
 // floor(hash * world / 2^64) on the top 32 bits.  Written with __umulhi: nvcc 12.9 turned the 64-bit form
 // (((h >> 32) * world) >> 32), used as a shared-memory index, into a low multiply (every record went to owner 0).
@@ -476,7 +477,8 @@ __global__ void __launch_bounds__(256) k_owner_scatter(OwnerArgs a)
         const u64 h = a.hash[i];
         const u32 o = owner_of_hash(h, a.world);
         const u32 p = basep[o] + atomicAdd(cnt + o, 1u);
-        a.send_hash[p] = h; a.send_index[p] = a.base_index + i; a.pos[i] = p;
+        reinterpret_cast<ulonglong2 *>(a.send_pairs)[p] = make_ulonglong2(h, a.base_index + i);
+        a.pos[i] = p;
     }
 }
 

@@ -312,10 +312,10 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
 u64 pow2_at_least(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
 
 int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, u32 *overflow,
-                 const u64 *hash, const u64 *index, u64 base, u32 n, u64 *slot_of)
+                 const u64 *hash, const u64 *index, u64 base, u32 n, u64 *slot_of, u32 stride = 1)
 {
     if (!n) return CK_OK;
-    TableArgs t{slots, nslots - 1, side, hash, index, base, n, slot_of, nullptr, overflow};
+    TableArgs t{slots, nslots - 1, side, hash, index, stride, base, n, slot_of, nullptr, overflow};
     k_table_insert<<<(n + 255) / 256, 256, 0, st>>>(t);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
@@ -324,7 +324,7 @@ int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64
 int table_first(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, const u64 *slot_of, u32 n, u64 *first)
 {
     if (!n) return CK_OK;
-    TableArgs t{slots, nslots - 1, side, nullptr, nullptr, 0, n, const_cast<u64 *>(slot_of), first, nullptr};
+    TableArgs t{slots, nslots - 1, side, nullptr, nullptr, 1, 0, n, const_cast<u64 *>(slot_of), first, nullptr};
     k_table_first<<<(n + 255) / 256, 256, 0, st>>>(t);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
@@ -719,14 +719,21 @@ int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_by
     if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
     return table_first(ctx, (cudaStream_t)stream, slots, nslots, side, U(slot_scratch), n, U(out_first_index));
 }
-int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, uint32_t world,
-                           uint64_t *send_hash, uint64_t *send_index, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host)
+int ck_dev_table_insert_pairs(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *pairs, uint32_t n,
+                              uint64_t *slot_scratch)
 {
-    if (!ctx || !hash64 || !send_hash || !send_index || !pos || !counts_dev || !counts_host || world < 1 || world > 32)
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !pairs || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
+    return table_insert(ctx, (cudaStream_t)stream, slots, nslots, side, ov, U(pairs), U(pairs) + 1, 0, n, U(slot_scratch), 2);
+}
+int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, uint32_t world,
+                           uint64_t *send_pairs, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host)
+{
+    if (!ctx || !hash64 || !send_pairs || !pos || !counts_dev || !counts_host || world < 1 || world > 32)
         return ctx ? fail(ctx, CK_ERR_ARG, "bad partition arguments") : CK_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     CK_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, 2 * world * sizeof(u32), st));
-    OwnerArgs a{U(hash64), n, world, base_index, counts_dev, U(send_hash), U(send_index), pos};
+    OwnerArgs a{U(hash64), n, world, base_index, counts_dev, U(send_pairs), pos};
     if (n) {
         const u32 grid = std::min<u32>((n + 255) / 256, 8u * (u32)ctx->num_sms);
         k_owner_count<<<grid, 256, 0, st>>>(a);

@@ -116,6 +116,11 @@ class DeviceTable:
         self.ctx._check(self.ctx._lib.ck_dev_table_insert(self.ctx.handle, _stream(), _p(self.buf), self.bytes,
                                                           _p(hash64), _p(index), base_index, n, _p(slot_scratch)))
 
+    def insert_pairs(self, pairs: torch.Tensor, n: int, slot_scratch: torch.Tensor):
+        """insert (hash64, index) rows of an int64[n, 2] tensor (what the hash-range exchange delivers)"""
+        self.ctx._check(self.ctx._lib.ck_dev_table_insert_pairs(self.ctx.handle, _stream(), _p(self.buf), self.bytes,
+                                                                _p(pairs), n, _p(slot_scratch)))
+
     def first(self, slot_scratch: torch.Tensor, n: int, out_first: torch.Tensor):
         self.ctx._check(self.ctx._lib.ck_dev_table_first(self.ctx.handle, _stream(), _p(self.buf), self.bytes,
                                                          _p(slot_scratch), n, _p(out_first)))
@@ -128,19 +133,18 @@ class OwnerPartitioner:
     def __init__(self, ctx: Context, n: int, world: int, dev=None):
         dev = dev or torch.device("cuda", ctx.device)
         self.ctx, self.world = ctx, world
-        self.h = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
-        self.i = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        self.pairs = torch.empty((max(n, 1), 2), dtype=torch.int64, device=dev)
         self.pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.counts_dev = torch.zeros(2 * world, dtype=torch.int32, device=dev)
         self.counts_host = (C.c_uint32 * world)()
 
     def __call__(self, hash64: torch.Tensor, base_index: int, world: int):
         n = hash64.numel()
-        assert world == self.world and n <= self.h.numel()
+        assert world == self.world and n <= self.pairs.shape[0]
         self.ctx._check(self.ctx._lib.ck_dev_owner_partition(self.ctx.handle, _stream(), _p(hash64), n, base_index, world,
-                                                             _p(self.h), _p(self.i), _p(self.pos), _p(self.counts_dev),
+                                                             _p(self.pairs), _p(self.pos), _p(self.counts_dev),
                                                              self.counts_host))
-        return self.h[:n], self.i[:n], self.pos[:n], [int(c) for c in self.counts_host]
+        return self.pairs[:n], self.pos[:n], [int(c) for c in self.counts_host]
 
 
 def kernel_times(ctx: Context):

@@ -24,7 +24,7 @@ def owner_of(hash64: torch.Tensor, world: int) -> torch.Tensor:
 
 
 def _all_to_all(send: torch.Tensor, send_counts: list[int], recv_counts: list[int], group=None) -> torch.Tensor:
-    recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
     backend = dist.get_backend(group)
     if backend == "nccl":
         dist.all_to_all_single(recv, send, recv_counts, send_counts, group=group)
@@ -48,7 +48,7 @@ def _all_to_all(send: torch.Tensor, send_counts: list[int], recv_counts: list[in
     for p in range(world):
         if p == rank or not recv_counts[p]:
             continue
-        bufs[p] = torch.empty(recv_counts[p], dtype=send.dtype, device=send.device)
+        bufs[p] = torch.empty((recv_counts[p],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         reqs.append(dist.irecv(bufs[p], p, group=group))
     for r in reqs:
         r.wait()
@@ -59,33 +59,33 @@ def _all_to_all(send: torch.Tensor, send_counts: list[int], recv_counts: list[in
 
 def exchange_first_index(hash64: torch.Tensor, base_index: int,
                          first_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], group=None,
-                         partition_fn=None) -> torch.Tensor:
+                         partition_fn=None, first_pairs_fn=None) -> torch.Tensor:
     """first_index[i] (global) for every local record i.
 
     hash64     int64[n]  XXH3-64 of the local records' canonical forms (bit pattern)
     base_index           global input index of local record 0 (shards are contiguous, rank order)
     first_fn(h, idx) ->  int64[m]: for the items this rank owns, the minimum global index per key
                          (idx None in the single-rank case: the index of item j is base_index + j)
-    partition_fn(h, base_index, world) -> (h_send, i_send, pos, send_counts): bucket by owner on the device
-                         (device.OwnerPartitioner); default: the same with torch ops (CPU tests)
+    partition_fn(h, base_index, world) -> (pairs int64[n, 2], pos, send_counts): bucket (hash, index) by owner on the
+                         device (device.OwnerPartitioner); default: the same with torch ops (CPU tests)
+    first_pairs_fn(pairs) -> int64[m]: first_fn over the received (hash, index) rows without splitting them
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = hash64.numel()
     if world == 1:
         return first_fn(hash64, None)                      # idx None: global index = base_index + position
-    gidx = None
     if partition_fn is not None:
-        h_send, i_send, pos, send_counts = partition_fn(hash64, base_index, world)
+        pairs, pos, send_counts = partition_fn(hash64, base_index, world)
         send_counts_t = torch.tensor(send_counts, dtype=torch.int64, device=hash64.device)
     else:
         owner = owner_of(hash64, world)
         order = torch.argsort(owner, stable=True)          # bucket by owner (order inside a bucket is free)
         send_counts_t = torch.bincount(owner, minlength=world)
         gidx = torch.arange(base_index, base_index + n, dtype=torch.int64, device=hash64.device)
-        h_send, i_send = hash64[order].contiguous(), gidx[order].contiguous()
+        pairs = torch.stack([hash64[order], gidx[order]], dim=1).contiguous()
         pos = torch.empty_like(order)
         pos[order] = torch.arange(n, dtype=order.dtype, device=order.device)
-        send_counts = None
+        send_counts = [int(x) for x in send_counts_t.tolist()]
     recv_counts_t = torch.empty_like(send_counts_t)
     if dist.get_backend(group) == "nccl":
         dist.all_to_all_single(recv_counts_t, send_counts_t, group=group)
@@ -93,11 +93,11 @@ def exchange_first_index(hash64: torch.Tensor, base_index: int,
         gathered = [torch.empty_like(send_counts_t) for _ in range(world)]
         dist.all_gather(gathered, send_counts_t, group=group)
         recv_counts_t = torch.stack(gathered)[:, dist.get_rank(group)].contiguous()
-    if send_counts is None:
-        send_counts = [int(x) for x in send_counts_t.tolist()]
     recv_counts = [int(x) for x in recv_counts_t.tolist()]
-    h_recv = _all_to_all(h_send, send_counts, recv_counts, group)
-    i_recv = _all_to_all(i_send, send_counts, recv_counts, group)
-    f_recv = first_fn(h_recv, i_recv)                      # owner side: min global index per key
+    p_recv = _all_to_all(pairs, send_counts, recv_counts, group)          # one exchange: 16 bytes per record
+    if first_pairs_fn is not None:
+        f_recv = first_pairs_fn(p_recv)                    # owner side: min global index per key
+    else:
+        f_recv = first_fn(p_recv[:, 0].contiguous(), p_recv[:, 1].contiguous())
     f_back = _all_to_all(f_recv.contiguous(), recv_counts, send_counts, group)
-    return f_back[pos.long()]                              # back to input order
+    return f_back[pos]                                     # back to input order

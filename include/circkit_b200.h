@@ -131,11 +131,14 @@ int ck_dev_table_insert(ck_ctx *ctx, void *stream, void *table, uint64_t table_b
 int ck_dev_table_first(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *slot_scratch,
                        uint32_t n, uint64_t *out_first_index);
 /* Multi-GPU uniq (hash-range owners, replaces the single `seen` map of src/uniq.rs:27 across ranks): bucket the local
- * (hash64, base_index + i) pairs by owner = floor(hash64 * world / 2^64) into per-owner runs of send_hash / send_index (the
- * send buffers of one personalised all-to-all); pos[i] = where record i went; counts_host[world] = records per owner
- * (the call synchronises the stream to return them).  counts_dev: 2 * world u32 of device scratch. */
+ * (hash64, base_index + i) pairs by owner = floor(hash64 * world / 2^64) into per-owner runs of send_pairs (2 u64 per record:
+ * the send buffer of one personalised all-to-all); pos[i] = where record i went; counts_host[world] = records per owner
+ * (the call synchronises the stream to return them).  counts_dev: 2 * world u32 of device scratch.
+ * ck_dev_table_insert_pairs: ck_dev_table_insert over such (hash64, index) pairs as they arrive at the owner. */
 int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, uint32_t world,
-                           uint64_t *send_hash, uint64_t *send_index, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host);
+                           uint64_t *send_pairs, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host);
+int ck_dev_table_insert_pairs(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *pairs, uint32_t n,
+                              uint64_t *slot_scratch);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ck_launch_count(const ck_ctx *ctx);
 /* per-class kernel timing for the roofline: when enabled, every length/alphabet-class launch is bracketed

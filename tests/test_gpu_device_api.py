@@ -181,11 +181,20 @@ def test_owner_partition_matches_owner_of(env, world):
     h = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
     h[:4] = torch.tensor([0, -1, 2**63 - 1, -2**63], dtype=torch.int64)
     part = D.OwnerPartitioner(ctx, n, world)
-    hs, is_, pos, counts = part(h, base, world)
+    pairs, pos, counts = part(h, base, world)
+    hs, is_ = pairs[:, 0], pairs[:, 1]
     own = owner_of(h, world)
     assert counts == torch.bincount(own, minlength=world).tolist()
     assert torch.equal(hs[pos.long()], h)
     assert torch.equal(is_[pos.long()], torch.arange(base, base + n, device="cuda"))
+    # the owner side over the same rows: first index per key == the table fed with separate arrays
+    t1, t2 = D.DeviceTable(ctx, n), D.DeviceTable(ctx, n)
+    s1 = torch.empty(n, dtype=torch.int64, device="cuda"); s2 = torch.empty_like(s1)
+    f1 = torch.empty_like(s1); f2 = torch.empty_like(s1)
+    dup = pairs.clone(); dup[n // 2:, 0] = dup[: n - n // 2, 0]            # force repeated keys
+    t1.insert_pairs(dup, n, s1); t1.first(s1, n, f1)
+    t2.insert(dup[:, 0].contiguous(), n, s2, index=dup[:, 1].contiguous()); t2.first(s2, n, f2)
+    assert torch.equal(f1, f2) and int((f1 != dup[:, 1]).sum()) > 0
     assert torch.equal(torch.sort(pos.long()).values, torch.arange(n, device="cuda"))
     starts = np.concatenate([[0], np.cumsum(counts)])
     o_sorted = owner_of(hs, world).cpu().numpy()
