@@ -74,10 +74,8 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
         cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32);
         cp_async8(head + 48, nb + 8 * s1); cp_async8(head + 56, nb + 8 * s1 + 8);
-        const u32 bytes = n1 >> 2;                                 // the rest of a short record -> L2
-        if (bytes > 64) prefetch_l2(nb + 64);
-        if (bytes > 128) prefetch_l2(nb + 128);
-        if (bytes > 192) prefetch_l2(nb + 192);
+        if (n1 <= 512u && n1 > 192u) prefetch_l2(nb + 64);         // short records (short batches): the rest of the record -> L2;
+                                                                   // a long batch outlives what L2 would keep
     };
 
     // (offset, end) of a record, or (offset, normalised length) when the batch carries lengths of its own
