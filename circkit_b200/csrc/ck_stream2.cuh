@@ -62,10 +62,8 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
     const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
     const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
     const u32 head = aux + CK_T2_AUX_BYTES + 1024u + 384u + 512u + 80u * lane;   // first three quads + last-step units of this lane's record
-    const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
     const u32 count = use_list ? *a.count : a.n_direct;
     if (use_list) a.list += a.count[16];
-    const u32 bstride = nw * 32u;
     const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
     // request the head of a record (quads 0..2 and the three units of its last scan step) into this lane's head slot: issued
     // one batch ahead, so no lane waits for the first touch of its record
@@ -86,10 +84,19 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         else cp_async8(offs + 512u * slot + 8u, a.offsets + rec + 1);
     };
     auto length_of = [&](const uint4 &oe) { return has_lens ? oe.z : oe.z - oe.x; };
-    // ---- prologue: offsets of batches 0 and 1, (work lists) record indices of batches 0..2
+    // Batches of 32 records are claimed from a launch-wide counter (a.retry_counts[28], zeroed with the class counters), so
+    // every warp stays busy until the work runs out.  A warp knows its next three batches: the offsets of batch kb + 2
+    // and the heads of batch kb + 1 are in flight while batch kb is processed.
+    auto claim = [&]() {
+        u32 v = 0;
+        if (lane == 0) v = atomicAdd(a.retry_counts + 28, 1u);
+        return __shfl_sync(CK_FULL, v, 0) * 32u;
+    };
+    // ---- prologue: offsets of batches 0 and 1, heads of batch 0, (work lists) record indices of batches 0..2
+    u32 b0 = claim(), b1 = claim(), b2 = claim();
     u32 rq = 0;                                                    // work lists: record index two batches ahead
     {
-        const u32 i0 = gw * 32u + lane, i1 = i0 + bstride, i2 = i1 + bstride;
+        const u32 i0 = b0 + lane, i1 = b1 + lane, i2 = b2 + lane;
         u32 r0 = i0, r1 = i1;
         if (use_list) {
             r0 = i0 < count ? a.list[i0] : 0u; r1 = i1 < count ? a.list[i1] : 0u; rq = i2 < count ? a.list[i2] : 0u;
@@ -105,10 +112,11 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         }
     }
     u32 kb = 0;                                                    // batch counter of this warp
-    for (u32 b = gw * 32u; b < count; b += bstride, kb++) {
+    for (; b0 < count; kb++) {
         const u32 sl = kb & 1u;
-        const u32 idx = b + lane;
+        const u32 idx = b0 + lane;
         const bool have = idx < count;
+        const u32 b3 = claim();
         cp_async_wait_all();
         __syncwarp();                                              // the offsets of batches kb and kb + 1 have landed
         u32 rec = idx; u64 off = 0; u32 n = 0;
@@ -116,19 +124,19 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
             const uint4 oe = lds128(offs + 512u * sl);
             if (use_list) rec = lds32(recs + 128u * (kb % 3u));
             if (have) { off = ((u64)oe.y << 32) | oe.x; n = length_of(oe); } else rec = 0;
-            const u32 idx2 = idx + 2 * bstride;
+            const u32 idx2 = b2 + lane;
             if (idx2 < count) fetch_offsets(use_list ? rq : idx2, sl);
             if (use_list) {
                 sts32(recs + 128u * ((kb + 2u) % 3u), rq);
-                const u32 idx3 = idx2 + bstride;
+                const u32 idx3 = b3 + lane;
                 rq = idx3 < count ? a.list[idx3] : 0u;
             }
         }
         // this batch's record heads (requested one batch ago), then the request for the next batch's
         const uint4 H0 = lds128(head), H1 = lds128(head + 16), H2 = lds128(head + 32), HT = lds128(head + 48);
-        if (idx + bstride < count) {
+        if (b1 + lane < count) {
             const uint4 oe = lds128(offs + 512u * (sl ^ 1u));
-            const u32 rec1 = use_list ? lds32(recs + 128u * ((kb + 1u) % 3u)) : idx + bstride;
+            const u32 rec1 = use_list ? lds32(recs + 128u * ((kb + 1u) % 3u)) : b1 + lane;
             fetch_head(((u64)oe.y << 32) | oe.x, length_of(oe), rec1);
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
@@ -393,6 +401,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
             a.retry[a.retry_counts[16 + c] + k] = rec;
         }
         __syncwarp();
+        b0 = b1; b1 = b2; b2 = b3;
     }
 }
 
