@@ -56,7 +56,10 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi needs
+    ~100 ms to come up and the timed region of the short configurations lasts a few ms, so the sampler starts early
+    (20 ms period) and `stop(t0, t1)` keeps the samples that arrived between the start of the warm-up and the end
+    of the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -67,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -75,15 +78,16 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = 0.0, t1: float = float("inf")):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        window = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.03]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -94,7 +98,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # median over the samples taken under load (upper half of the clock samples)
+        # median over the samples taken under load (upper half of the clock samples in the window)
         load = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
@@ -202,6 +206,8 @@ def main():
     ctx = circkit_b200.Context(device=local_rank, max_batch_bytes=(256 << 20) if not args.no_e2e else 0,
                                max_batch_records=(1 << 20) if not args.no_e2e else 0,
                                table_capacity=R if (w["uniq"] and not args.no_e2e) else 0)
+    sampler = ClockSampler(local_rank)                     # started early: nvidia-smi needs ~100 ms to come up
+    sampler.start()
     base_index = rank * R
     batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
                           dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
@@ -248,8 +254,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)                     # started before the warm-up: nvidia-smi needs ~100 ms to come up
-    sampler.start()
+    t_window0 = time.time()
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -265,7 +270,7 @@ def main():
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_window0, time.time())
     launches = ctx.launch_count() - launches0
     ktimes = D.kernel_times(ctx)
     ctx._lib.ck_kernel_timing(ctx.handle, 0)
