@@ -32,12 +32,14 @@ WORKLOADS = {
                desc="config 1: canonicalize, 1M viroid-length (250-400 nt) records"),
     "c2": dict(records=10_000_000, kind=1, lo=200, hi=5000, dup=300, adv=0, uniq=True,
                desc="config 2: uniq, 10M circRNA-length (0.2-5 kb log-uniform) records, 30% rotated/revcomp duplicates"),
+    "c3": dict(records=5_000_000, kind=0, lo=250, hi=400, dup=0, adv=0, uniq=False, raw=True,
+               desc="config 3: canonicalize, 5M mixed IUPAC/N records (byte-level lanes, CLI semantics: normalise on device)"),
     "c4": dict(records=200_000, kind=1, lo=5000, hi=200_000, dup=0, adv=10, uniq=False,
                desc="config 4: canonicalize, 200k plasmid/mtDNA-length (5-200 kb) records, 1% adversarial repeats"),
     "c5": dict(records=12_500_000, kind=0, lo=250, hi=400, dup=300, adv=0, uniq=True,
                desc="config 5: uniq, 100M viroid-length records over 8 GPUs (12.5M per GPU), 30% duplicates"),
 }
-SEEDS = {"c1": 1, "c2": 2, "c4": 4, "c5": 5}
+SEEDS = {"c1": 1, "c2": 2, "c3": 3, "c4": 4, "c5": 5}
 
 
 def parse_args():
@@ -209,10 +211,33 @@ def main():
     sampler = ClockSampler(local_rank)                     # started early: nvidia-smi needs ~100 ms to come up
     sampler.start()
     base_index = rank * R
-    batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
-                          dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
+    raw_dev = None
+    if w.get("raw"):
+        # config 3: raw record bytes resident in HBM (numpy generator circkit_b200/synth_host.py, 500 k distinct records tiled to
+        # the requested count -- generating 5 M on the host would take minutes); every symbol lane is exercised:
+        # normalise + classify + pack + canonicalise per step
+        import numpy as np
+        from circkit_b200 import synth_host
+        tile_n = min(R, 500_000)
+        a_np, o_np = synth_host.make_iupac_records(tile_n, w["lo"], w["hi"], seed + rank)
+        reps = (R + tile_n - 1) // tile_n
+        a_t = torch.from_numpy(a_np).to(dev)
+        l_t = torch.from_numpy((o_np[1:] - o_np[:-1]).astype(np.int64)).to(dev)
+        raw_dev = a_t.repeat(reps)
+        lens_all = l_t.repeat(reps)[:R]
+        offs = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens_all, 0, out=offs[1:])
+        total_raw = int(offs[-1].item())
+        raw_dev = raw_dev[:total_raw].contiguous()
+        batch = D.DeviceBatch(offs, None, R, total_raw)
+        lens_out = torch.empty(R, dtype=torch.int32, device=dev)
+        ws = D.Workspace(ctx, R, total_raw, dev)
+        w["mask"] = 0
+    else:
+        batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
+                              dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
+        ws = D.Workspace(ctx, R, 0, dev)
     outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"], aligned=True)
-    ws = D.Workspace(ctx, R, 0, dev)
     lens = batch.lens
     if w["uniq"]:
         table = D.DeviceTable(ctx, capacity_keys=int(R * 1.05) + 1024, dev=dev)   # owns ~R keys of the global set
@@ -242,7 +267,10 @@ def main():
         return out[:m]
 
     def step():
-        D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
+        if raw_dev is not None:
+            D.canon_bytes(ctx, raw_dev, batch.offsets, R, batch.total, outs, lens_out, ws, normalize=True)
+        else:
+            D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
         if w["uniq"]:
             table.clear()
             f = X.exchange_first_index(outs.hash[:R], base_index, first_fn, partition_fn=partitioner, first_pairs_fn=first_pairs_fn)
@@ -292,10 +320,14 @@ def main():
     from circkit_b200.device import CLASS_NAMES
     dom = max((c for c in CLASS_NAMES if ktimes[c][1]), key=lambda c: ktimes[c][0])
     lo_n, hi_n = D.CLASS_RANGE.get(dom, (1, 1 << 40))
+    byte_lane = dom.startswith(("4bit", "byte"))
     # bytes this kernel's launch moves by the algorithm: packed read + ASCII write + 16 (+8 hash write);
     # the table's 32 B/record belong to the table kernels, not to this launch
     sel = lens[(lens >= lo_n) & (lens <= hi_n)]
-    alg_bytes = int((8 * ((sel + 31) // 32) + sel + 16 + (8 if w["uniq"] else 0)).sum().item())
+    if byte_lane:        # byte lanes: n bytes read + n bytes written + 16; every record of the batch charged to the lane
+        alg_bytes = int((2 * sel + 16).sum().item())
+    else:
+        alg_bytes = int((8 * ((sel + 31) // 32) + sel + 16 + (8 if w["uniq"] else 0)).sum().item())
     dom_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -311,7 +343,7 @@ def main():
         except Exception:
             traffic = None
     kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
-    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_s2 (lane per record, streaming)", dom),
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s2 (lane per record, streaming)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,
@@ -322,7 +354,7 @@ def main():
     if not args.no_e2e:
         import ctypes as C
         import numpy as np
-        ascii_dev = D.unpack_ascii(ctx, batch)
+        ascii_dev = raw_dev if raw_dev is not None else D.unpack_ascii(ctx, batch)
         total = int(batch.total)
         lib = ctx._lib
         h_bytes_p = lib.ck_alloc_pinned(ctx.handle, total + 64)
@@ -354,7 +386,9 @@ def main():
         out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
         out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
         out_strand_p = lib.ck_alloc_pinned(ctx.handle, (R + 1))
-        flags = 2   # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record
+        # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record (config 3:
+        # + CK_F_NORMALIZE, the CLI path)
+        flags = 2 | (1 if raw_dev is not None else 0)
 
         def e2e_step():
             if w["uniq"]:

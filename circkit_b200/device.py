@@ -15,6 +15,7 @@ from .core import Context
 CLASS_NAMES = ["2bit_le_512", "2bit_le_2048", "2bit_le_65536", "2bit_le_425984", "4bit_le_2048", "4bit_le_212992",
                "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192", "2bit_lane_128_8192"]
 # length range [lo, hi] of each 2-bit class (class_mask bit = index in CLASS_NAMES)
+BYTE_CLASSES = ("4bit_le_2048", "4bit_le_212992", "byte_le_1024", "byte_le_106496")
 CLASS_RANGE = {"2bit_le_512": (1, 512), "2bit_le_2048": (513, 2048), "2bit_le_4096": (2049, 4096), "2bit_le_8192": (4097, 8192),
                "2bit_le_65536": (8193, 65536), "2bit_le_425984": (65537, 425984), "2bit_lane_128_8192": (1, 8192)}
 
@@ -93,6 +94,17 @@ def canon_packed2(ctx: Context, b: DeviceBatch, outs: CanonOutputs, ws: Workspac
     ctx._check(ctx._lib.ck_dev_canon_packed2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), b.n, flags, class_mask,
                                              _p(outs.out), _p(outs.start), _p(outs.strand), _p(outs.hash),
                                              _p(ws.buf), ws.bytes))
+
+
+def canon_bytes(ctx: Context, raw: torch.Tensor, offsets: torch.Tensor, n: int, total: int, outs: CanonOutputs,
+                lens_out: torch.Tensor, ws: Workspace, normalize: bool, class_mask: int = 0):
+    """normalise + classify + pack + canonicalise a resident batch of raw record bytes (every symbol lane): the
+    worker closure of src/canonicalize.rs:21-30 on HBM-resident input (no copies, no sync)."""
+    flags = ((N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_ALIGNED_OUT if outs.aligned else 0)
+             | (0 if outs.out is not None else N.CK_F_NO_BYTES))
+    ctx._check(ctx._lib.ck_dev_canon_bytes(ctx.handle, _stream(), _p(raw), _p(offsets), n, total, flags, class_mask,
+                                           _p(outs.out), _p(lens_out), _p(outs.start), _p(outs.strand), _p(outs.hash),
+                                           _p(ws.buf), ws.bytes))
 
 
 def check(ctx: Context, ws: Workspace):

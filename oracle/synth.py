@@ -43,3 +43,4 @@ def make_records(n_records: int, kind: int, lo: int, hi: int, dup_permille: int,
             t = _COMP[t[::-1]]
         arena[int(offsets[i]): int(offsets[i + 1])] = t
     return arena, offsets
+

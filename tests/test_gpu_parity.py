@@ -173,6 +173,17 @@ def test_random_and_structured_records_all_lanes(ctx, alpha, normalize):
     _check_batch(ctx, seqs, normalize, tag=repr(alpha))
 
 
+@pytest.mark.parametrize("normalize", [True, False], ids=["cli-semantics", "lib-semantics"])
+def test_config3_shape_iupac_records(ctx, normalize):
+    """BASELINE config 3 (mixed IUPAC / N records, byte-level lanes) at 20 k records: CLI semantics (needletail
+    normalisation: IUPAC -> N, lowercase -> upper, U -> T; 4-bit lane) and library semantics (bytes as they are, bio's
+    complement table; 4-bit lane for upper-case IUPAC, byte lane for soft-masked / RNA records)."""
+    from circkit_b200 import synth_host
+    arena, off = synth_host.make_iupac_records(20000, 250, 400, seed=3)
+    seqs = [arena[int(off[i]): int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
+    _check_batch(ctx, seqs, normalize, tag="config 3 " + ("cli" if normalize else "lib"))
+
+
 def test_long_records_cta_shape(ctx):
     rng = random.Random(9)
     seqs = []
