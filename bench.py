@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="multi-GPU uniq: sub-batches per rank, the exchange of one overlapping the kernels of the next "
+                         "(measured at 2 GPUs: 2 or 4 sub-batches are slower than 1 -- smaller launches, more collectives)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline measurement")
@@ -211,7 +214,7 @@ def main():
     sampler = ClockSampler(local_rank)                     # started early: nvidia-smi needs ~100 ms to come up
     sampler.start()
     base_index = rank * R
-    raw_dev = None
+    raw_dev, subs = None, None
     if w.get("raw"):
         # config 3: raw record bytes resident in HBM (numpy generator circkit_b200/synth_host.py, 500 k distinct records tiled to
         # the requested count -- generating 5 M on the host would take minutes); every symbol lane is exercised:
@@ -233,17 +236,34 @@ def main():
         lens_out = torch.empty(R, dtype=torch.int32, device=dev)
         ws = D.Workspace(ctx, R, total_raw, dev)
         w["mask"] = 0
+    elif w["uniq"] and world > 1:
+        # multi-GPU uniq: the rank's shard as `chunks` sub-batches, so that the hash-range exchange of one sub-batch overlaps
+        # the canonicalisation of the next (same records, same order: record g is a pure function of (seed, g))
+        C = max(1, min(args.chunks, R))
+        bounds = [R * c // C for c in range(C + 1)]
+        subs, parts, run = [], [], 0
+        for c in range(C):
+            n_c = bounds[c + 1] - bounds[c]
+            b_c = D.synth_batch(ctx, seed=seed, first_index=base_index + bounds[c], n_records=n_c, kind=w["kind"], lo=w["lo"],
+                                hi=w["hi"], dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
+            subs.append(dict(b=b_c, n=n_c, lo=bounds[c], base=base_index + bounds[c], ws=D.Workspace(ctx, n_c, 0, dev),
+                             outs=D.CanonOutputs(n_c, b_c.total, dev, want_bytes=True, want_hash=True, aligned=True),
+                             part=D.OwnerPartitioner(ctx, n_c, world, dev), ev=torch.cuda.Event()))
+            parts.append(b_c.offsets[:-1] + run)
+            run += b_c.total
+        parts.append(torch.tensor([run], dtype=torch.int64, device=dev))
+        batch = D.DeviceBatch(torch.cat(parts), None, R, run)      # offsets of the whole shard (sizes, e2e)
+        ws = None
     else:
         batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
                               dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
         ws = D.Workspace(ctx, R, 0, dev)
-    outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"], aligned=True)
+    outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"], aligned=True) if subs is None else None
     lens = batch.lens
     if w["uniq"]:
         table = D.DeviceTable(ctx, capacity_keys=int(R * 1.05) + 1024, dev=dev)   # owns ~R keys of the global set
         first = torch.empty(R, dtype=torch.int64, device=dev)
         slot_cache = {}
-        partitioner = D.OwnerPartitioner(ctx, R, world, dev) if world > 1 else None
 
         def first_fn(h, idx):
             m = h.numel()
@@ -256,25 +276,53 @@ def main():
             table.first(slots, m, out)
             return out[:m]
 
-    def first_pairs_fn(pairs):
-        m = pairs.shape[0]
-        if m not in slot_cache:
-            slot_cache[m] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
-                             torch.empty(max(m, 1), dtype=torch.int64, device=dev))
-        slots, out = slot_cache[m]
-        table.insert_pairs(pairs, m, slots)
-        table.first(slots, m, out)
-        return out[:m]
+        def insert_pairs_fn(pairs):                 # owner side, phase 1: returns the slots for the later query
+            m = pairs.shape[0]
+            slots = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+            table.insert_pairs(pairs, m, slots)
+            return slots
+
+        def first_query_fn(slots, m):               # owner side, phase 2
+            out = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+            table.first(slots, m, out)
+            return out[:m]
+
+    comm = torch.cuda.Stream(device=dev) if subs is not None else None
 
     def step():
+        if subs is not None:
+            cur = torch.cuda.current_stream()
+            table.clear()
+            comm.wait_stream(cur)                   # the cleared table before any insert
+            pend = []
+
+            def send(sb):
+                with torch.cuda.stream(comm):
+                    comm.wait_event(sb["ev"])
+                    return X.exchange_send(sb["outs"].hash[:sb["n"]], sb["base"], sb["part"], insert_pairs_fn)
+
+            for c, sb in enumerate(subs):
+                D.canon_packed2(ctx, sb["b"], sb["outs"], sb["ws"], class_mask=w["mask"])
+                sb["ev"].record(cur)
+                if c >= 1:
+                    pend.append(send(subs[c - 1]))  # exchange of sub-batch c-1 while sub-batch c is canonicalised
+            pend.append(send(subs[-1]))
+            with torch.cuda.stream(comm):           # every insert of every rank has landed: first index per record
+                for sb, p in zip(subs, pend):
+                    first[sb["lo"]: sb["lo"] + sb["n"]].copy_(X.exchange_finish(p, first_query_fn))
+            cur.wait_stream(comm)
+            return
         if raw_dev is not None:
             D.canon_bytes(ctx, raw_dev, batch.offsets, R, batch.total, outs, lens_out, ws, normalize=True)
         else:
             D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
         if w["uniq"]:
             table.clear()
-            f = X.exchange_first_index(outs.hash[:R], base_index, first_fn, partition_fn=partitioner, first_pairs_fn=first_pairs_fn)
-            first.copy_(f)
+            first.copy_(X.exchange_first_index(outs.hash[:R], base_index, first_fn))
+
+    def check_all():
+        for wsp in ([sb["ws"] for sb in subs] if subs is not None else [ws]):
+            D.check(ctx, wsp)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -286,7 +334,7 @@ def main():
     for _ in range(args.warmup):
         step()
     sync_all()
-    D.check(ctx, ws)
+    check_all()
     ctx._lib.ck_kernel_timing(ctx.handle, 1)
     D.kernel_times(ctx)
     launches0 = ctx.launch_count()
@@ -302,7 +350,7 @@ def main():
     launches = ctx.launch_count() - launches0
     ktimes = D.kernel_times(ctx)
     ctx._lib.ck_kernel_timing(ctx.handle, 0)
-    D.check(ctx, ws)
+    check_all()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,7 +376,8 @@ def main():
         alg_bytes = int((2 * sel + 16).sum().item())
     else:
         alg_bytes = int((8 * ((sel + 31) // 32) + sel + 16 + (8 if w["uniq"] else 0)).sum().item())
-    dom_ms = ktimes[dom][0] / max(ktimes[dom][1], 1)
+    launches_per_step = max(ktimes[dom][1], 1) / args.steps          # > 1 when the shard runs as sub-batches
+    dom_ms = ktimes[dom][0] / args.steps                              # per step: all launches of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -340,12 +389,15 @@ def main():
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            if traffic is not None:
+                traffic = int(traffic / launches_per_step)
         except Exception:
             traffic = None
     kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
     roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s2 (lane per record, streaming)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_ms,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes / launches_per_step),
+                "kernel_ms_per_launch": dom_ms / launches_per_step, "launches_per_step": launches_per_step,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,
                 "step_ms": ms_per_step}
 
@@ -354,7 +406,12 @@ def main():
     if not args.no_e2e:
         import ctypes as C
         import numpy as np
-        ascii_dev = raw_dev if raw_dev is not None else D.unpack_ascii(ctx, batch)
+        if raw_dev is not None:
+            ascii_dev = raw_dev
+        elif subs is not None:
+            ascii_dev = torch.cat([D.unpack_ascii(ctx, sb["b"]) for sb in subs])
+        else:
+            ascii_dev = D.unpack_ascii(ctx, batch)
         total = int(batch.total)
         lib = ctx._lib
         h_bytes_p = lib.ck_alloc_pinned(ctx.handle, total + 64)

@@ -57,6 +57,19 @@ def _all_to_all(send: torch.Tensor, send_counts: list[int], recv_counts: list[in
     return recv
 
 
+def _exchange_counts(send_counts_t: torch.Tensor, group=None) -> list[int]:
+    """how many items every peer sends to this rank"""
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        recv_counts_t = torch.empty_like(send_counts_t)
+        dist.all_to_all_single(recv_counts_t, send_counts_t, group=group)
+    else:
+        gathered = [torch.empty_like(send_counts_t) for _ in range(world)]
+        dist.all_gather(gathered, send_counts_t, group=group)
+        recv_counts_t = torch.stack(gathered)[:, dist.get_rank(group)].contiguous()
+    return [int(x) for x in recv_counts_t.tolist()]
+
+
 def exchange_first_index(hash64: torch.Tensor, base_index: int,
                          first_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], group=None,
                          partition_fn=None, first_pairs_fn=None) -> torch.Tensor:
@@ -86,14 +99,7 @@ def exchange_first_index(hash64: torch.Tensor, base_index: int,
         pos = torch.empty_like(order)
         pos[order] = torch.arange(n, dtype=order.dtype, device=order.device)
         send_counts = [int(x) for x in send_counts_t.tolist()]
-    recv_counts_t = torch.empty_like(send_counts_t)
-    if dist.get_backend(group) == "nccl":
-        dist.all_to_all_single(recv_counts_t, send_counts_t, group=group)
-    else:
-        gathered = [torch.empty_like(send_counts_t) for _ in range(world)]
-        dist.all_gather(gathered, send_counts_t, group=group)
-        recv_counts_t = torch.stack(gathered)[:, dist.get_rank(group)].contiguous()
-    recv_counts = [int(x) for x in recv_counts_t.tolist()]
+    recv_counts = _exchange_counts(send_counts_t, group)
     p_recv = _all_to_all(pairs, send_counts, recv_counts, group)          # one exchange: 16 bytes per record
     if first_pairs_fn is not None:
         f_recv = first_pairs_fn(p_recv)                    # owner side: min global index per key
@@ -101,3 +107,33 @@ def exchange_first_index(hash64: torch.Tensor, base_index: int,
         f_recv = first_fn(p_recv[:, 0].contiguous(), p_recv[:, 1].contiguous())
     f_back = _all_to_all(f_recv.contiguous(), recv_counts, send_counts, group)
     return f_back[pos]                                     # back to input order
+
+
+# ---- the same exchange in two phases, so that a rank can overlap it with the canonicalisation of its next sub-batch ----
+class PendingExchange:
+    """State between exchange_send and exchange_finish: where every local record went and what this rank received."""
+    __slots__ = ("pos", "send_counts", "recv_counts", "handle", "m")
+
+    def __init__(self, pos, send_counts, recv_counts, handle, m):
+        self.pos, self.send_counts, self.recv_counts, self.handle, self.m = pos, send_counts, recv_counts, handle, m
+
+
+def exchange_send(hash64: torch.Tensor, base_index: int, partition_fn, insert_pairs_fn, group=None) -> PendingExchange:
+    """Phase 1: bucket the local (hash, global index) pairs by owner, deliver them with one all-to-all and insert what
+    arrives into this rank's first-occurrence table (insert_pairs_fn(pairs) -> handle for the later query).  The table
+    keeps the minimum index per key, so phase 1 of any number of sub-batches may run in any order on any rank."""
+    world = dist.get_world_size(group)
+    pairs, pos, send_counts = partition_fn(hash64, base_index, world)
+    send_counts_t = torch.tensor(send_counts, dtype=torch.int64, device=hash64.device)
+    recv_counts = _exchange_counts(send_counts_t, group)
+    p_recv = _all_to_all(pairs, send_counts, recv_counts, group)
+    return PendingExchange(pos, send_counts, recv_counts, insert_pairs_fn(p_recv), p_recv.shape[0])
+
+
+def exchange_finish(p: PendingExchange, first_query_fn, group=None) -> torch.Tensor:
+    """Phase 2, after phase 1 of EVERY sub-batch has completed on this rank (all-to-alls are collective, so by then
+    every pair owned by this rank has been inserted): first_query_fn(handle, m) -> int64[m] first index of the received
+    pairs; a reverse all-to-all returns them; the result is first_index of the local records in input order."""
+    f_recv = first_query_fn(p.handle, p.m)
+    f_back = _all_to_all(f_recv.contiguous(), p.recv_counts, p.send_counts, group)
+    return f_back[p.pos]

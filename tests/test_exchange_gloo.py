@@ -45,6 +45,71 @@ def _worker(rank, world, port, hashes, expected, q):
     dist.destroy_process_group()
 
 
+def _torch_partition(h, base_index, world):
+    """stand-in for device.OwnerPartitioner (ck_dev_owner_partition)"""
+    from circkit_b200.exchange import owner_of
+    owner = owner_of(h, world)
+    order = torch.argsort(owner, stable=True)
+    gidx = torch.arange(base_index, base_index + h.numel(), dtype=torch.int64)
+    pairs = torch.stack([h[order], gidx[order]], dim=1).contiguous()
+    pos = torch.empty_like(order)
+    pos[order] = torch.arange(h.numel())
+    return pairs, pos, torch.bincount(owner, minlength=world).tolist()
+
+
+def _worker_two_phase(rank, world, port, hashes, expected, q):
+    """the shard as three sub-batches: phase 1 (send + insert) of all of them, then phase 2 (query + return), as
+    bench.py overlaps them on GPUs; the owner's table is a dict (min index per key, any insertion order)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from circkit_b200 import exchange as X
+    n = len(hashes) // world
+    lo, hi = rank * n, (rank + 1) * n if rank < world - 1 else len(hashes)
+    table = {}
+
+    def insert_pairs(pairs):
+        for k, i in pairs.tolist():
+            table[k] = min(table.get(k, i), i)
+        return pairs[:, 0].clone()
+
+    def query(keys, m):
+        return torch.tensor([table[k] for k in keys.tolist()], dtype=torch.int64)
+
+    cuts = [lo, lo + (hi - lo) // 3, lo + 2 * (hi - lo) // 3, hi]
+    pend = []
+    for a, b in reversed(list(zip(cuts[:-1], cuts[1:]))):          # any order of the sub-batches gives the same answer
+        h = torch.from_numpy(hashes[a:b].view(np.int64).copy())
+        pend.append((a, b, X.exchange_send(h, a, _torch_partition, insert_pairs)))
+    ok = True
+    for a, b, p in pend:
+        first = X.exchange_finish(p, query)
+        ok = ok and np.array_equal(first.numpy().astype(np.uint64), expected[a:b])
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_phase_exchange_matches_serial_consumer(world):
+    import oracle
+    from oracle import synth
+    arena, off = synth.make_records(2500, 0, 60, 120, 400, seed=10 + world)
+    res = oracle.canonicalize_batch(arena, off, normalize=True, threads=2, want_start=False)
+    hashes, expected = oracle.uniq_consume(res["out"], off, res["lens"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_two_phase, args=(r, world, port, hashes.copy(), expected, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(r, True) for r in range(world)]
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_exchange_matches_serial_consumer(world):
     import oracle
