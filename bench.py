@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=1,
                     help="multi-GPU uniq: sub-batches per rank, the exchange of one overlapping the kernels of the next "
                          "(measured at 2 GPUs: 2 or 4 sub-batches are slower than 1 -- smaller launches, more collectives)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="uniq: run the table / exchange stage of a step on the same stream as its kernels (default: on a second "
+                         "stream, overlapping the canonicalisation of the next step, double-buffered outputs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline measurement")
@@ -236,8 +239,8 @@ def main():
         lens_out = torch.empty(R, dtype=torch.int32, device=dev)
         ws = D.Workspace(ctx, R, total_raw, dev)
         w["mask"] = 0
-    elif w["uniq"] and world > 1:
-        # multi-GPU uniq: the rank's shard as `chunks` sub-batches, so that the hash-range exchange of one sub-batch overlaps
+    elif w["uniq"] and world > 1 and args.chunks > 1:
+        # (experiment, slower than the default) multi-GPU uniq: the rank's shard as `chunks` sub-batches, so that the hash-range exchange of one sub-batch overlaps
         # the canonicalisation of the next (same records, same order: record g is a pure function of (seed, g))
         C = max(1, min(args.chunks, R))
         bounds = [R * c // C for c in range(C + 1)]
@@ -288,6 +291,14 @@ def main():
             return out[:m]
 
     comm = torch.cuda.Stream(device=dev) if subs is not None else None
+    stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
+    if w["uniq"] and subs is None and raw_dev is None:
+        overlap = not args.no_overlap
+        stage_stream = torch.cuda.Stream(device=dev) if overlap else None
+        outs_sets = [outs, D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=True, aligned=True) if overlap else outs]
+        first_sets = [first, torch.empty_like(first) if overlap else first]
+        pipe = dict(k=0, done=[torch.cuda.Event(), torch.cuda.Event()], canon=[torch.cuda.Event(), torch.cuda.Event()])
+        partitioner = D.OwnerPartitioner(ctx, R, world, dev) if world > 1 else None
 
     def step():
         if subs is not None:
@@ -314,11 +325,33 @@ def main():
             return
         if raw_dev is not None:
             D.canon_bytes(ctx, raw_dev, batch.offsets, R, batch.total, outs, lens_out, ws, normalize=True)
-        else:
+            return
+        if not w["uniq"]:
             D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
-        if w["uniq"]:
+            return
+        # uniq: kernels of step k on the current stream into output set k & 1; its table / exchange stage on `stage_stream`
+        # (the same stream with --no-overlap), so that it overlaps the kernels of step k + 1
+        i = pipe["k"] & 1
+        pipe["k"] += 1
+        o_i, f_i = outs_sets[i], first_sets[i]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(pipe["done"][i])             # the stage of step k - 2 has finished with this output set
+        D.canon_packed2(ctx, batch, o_i, ws, class_mask=w["mask"])
+        pipe["canon"][i].record(cur)
+        st = stage_stream if stage_stream is not None else cur
+        with torch.cuda.stream(st):
+            st.wait_event(pipe["canon"][i])
             table.clear()
-            first.copy_(X.exchange_first_index(outs.hash[:R], base_index, first_fn))
+            if world == 1:
+                f_i.copy_(first_fn(o_i.hash[:R], None))
+            else:
+                pend = X.exchange_send(o_i.hash[:R], base_index, partitioner, insert_pairs_fn)
+                f_i.copy_(X.exchange_finish(pend, first_query_fn))
+            pipe["done"][i].record(st)
+
+    def drain():
+        if stage_stream is not None:
+            torch.cuda.current_stream().wait_stream(stage_stream)
 
     def check_all():
         for wsp in ([sb["ws"] for sb in subs] if subs is not None else [ws]):
@@ -333,6 +366,7 @@ def main():
     t_window0 = time.time()
     for _ in range(args.warmup):
         step()
+    drain()
     sync_all()
     check_all()
     ctx._lib.ck_kernel_timing(ctx.handle, 1)
@@ -343,9 +377,12 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    if pipe is not None:
+        first = first_sets[(pipe["k"] - 1) & 1]             # result of the last step
     clocks = sampler.stop(t_window0, time.time())
     launches = ctx.launch_count() - launches0
     ktimes = D.kernel_times(ctx)
