@@ -449,20 +449,25 @@ def main():
             ascii_dev = torch.cat([D.unpack_ascii(ctx, sb["b"]) for sb in subs])
         else:
             ascii_dev = D.unpack_ascii(ctx, batch)
-        total = int(batch.total)
+        off_host = batch.offsets.cpu().numpy().astype(np.uint64)
+        # multi-rank runs: every rank pins its own copy of the input; bound it to 4 GiB of record bytes per rank (the first
+        # R_e records of the shard -- the same steady-state batches, fewer of them)
+        R_e = R
+        if world > 1 and int(off_host[R]) > (4 << 30):
+            R_e = max(1, int(np.searchsorted(off_host, 4 << 30, side="right")) - 1)
+        total = int(off_host[R_e])
         lib = ctx._lib
         h_bytes_p = lib.ck_alloc_pinned(ctx.handle, total + 64)
         h_bytes = np.ctypeslib.as_array(C.cast(h_bytes_p, C.POINTER(C.c_uint8)), shape=(total + 64,))
         pinned_view = torch.from_numpy(h_bytes)
-        pinned_view[:total].copy_(ascii_dev)
+        pinned_view[:total].copy_(ascii_dev[:total])
         del ascii_dev
-        off_host = batch.offsets.cpu().numpy().astype(np.uint64)
         # batches of <= 256 MiB / <= 1 Mi records, alternating the two slots
         max_b, max_r = 256 << 20, 1 << 20
         cuts = [0]
-        while cuts[-1] < R:
+        while cuts[-1] < R_e:
             lo_i = cuts[-1]
-            hi_i = min(R, lo_i + max_r)
+            hi_i = min(R_e, lo_i + max_r)
             limit = int(off_host[lo_i]) + max_b
             if int(off_host[hi_i]) > limit:
                 hi_i = int(np.searchsorted(off_host, limit, side="right")) - 1
@@ -475,11 +480,11 @@ def main():
             arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(len(ro),))
             arr[:] = ro
             rel_offs.append(arr); pins.append(p)
-        out_first_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R + 1))
-        out_hash_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R + 1))
-        out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
-        out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R + 1))
-        out_strand_p = lib.ck_alloc_pinned(ctx.handle, (R + 1))
+        out_first_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R_e + 1))
+        out_hash_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R_e + 1))
+        out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R_e + 1))
+        out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R_e + 1))
+        out_strand_p = lib.ck_alloc_pinned(ctx.handle, (R_e + 1))
         # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record (config 3:
         # + CK_F_NORMALIZE, the CLI path)
         flags = 2 | (1 if raw_dev is not None else 0)
@@ -518,18 +523,18 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = total + 8 * (R + nb)
-        d2h = (R * (8 + 8 + 4)) if w["uniq"] else (R * (4 + 4 + 1))
+        h2d = total + 8 * (R_e + nb)
+        d2h = (R_e * (8 + 8 + 4)) if w["uniq"] else (R_e * (4 + 4 + 1))
         # parity spot check of the e2e result against the device-resident result (multi-rank: local keys only)
         if w["uniq"] and world == 1:
-            got = np.ctypeslib.as_array(C.cast(out_first_p, C.POINTER(C.c_uint64)), shape=(R,))
+            got = np.ctypeslib.as_array(C.cast(out_first_p, C.POINTER(C.c_uint64)), shape=(R_e,))
             assert np.array_equal(got, first.cpu().numpy().astype(np.uint64)), "e2e first_index != resident first_index"
-        e2e = {"value": total_records / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": R_e * world / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "batches_per_step": nb,
                "api": "ck_uniq_submit/ck_uniq_wait" if w["uniq"] else "ck_canon_submit/ck_canon_wait",
                "input": "ASCII record bytes + offsets in pinned host memory (normalise+pack on device)",
                "result": "first_index + hash64 + length per record" if w["uniq"] else "start + strand + length per record",
-               "gbases_per_s": total_bases / (dt / e2e_steps) / 1e9,
+               "gbases_per_s": total * world / (dt / e2e_steps) / 1e9, "records_per_gpu_per_step": R_e,
                "note": "multi-rank e2e dedups per rank (no exchange); the resident path does the global exchange" if world > 1 else ""}
         for p in pins + [out_first_p, out_hash_p, out_len_p, out_start_p, out_strand_p, h_bytes_p]:
             lib.ck_free_pinned(ctx.handle, p)
