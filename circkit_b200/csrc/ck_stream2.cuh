@@ -32,7 +32,7 @@
 namespace ck {
 
 #define CK_S2_WARPS 8u
-#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u + 512u + 2560u)
+#define CK_S2_WARP_BYTES (CK_T2_AUX_BYTES + 1024u + 384u + 2560u)
 
 __device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 // same load as an asm volatile statement: the compiler must leave it where it is written (it would otherwise sink a
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
     const u32 aux = (u32)__cvta_generic_to_shared(smem) + wid * CK_S2_WARP_BYTES;   // output stage
     const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
     const u32 recs = aux + CK_T2_AUX_BYTES + 1024u + 4u * lane;    // + 128 * (batch % 3): record index (work lists)
-    const u32 head = aux + CK_T2_AUX_BYTES + 1024u + 384u + 512u + 80u * lane;   // first three quads + last-step units of this lane's record
+    const u32 head = aux + CK_T2_AUX_BYTES + 1024u + 384u + 80u * lane;   // first three quads + last-step units of this lane's record
     const u32 count = use_list ? *a.count : a.n_direct;
     if (use_list) a.list += a.count[16];
     const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
@@ -259,12 +259,16 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
             const u32 nbr = (want_hash && fast && nn <= 240u) ? nn >> 4 : 0u;    // rounds of 16 bytes
             const bool any_mid = want_hash && __any_sync(CK_FULL, nbr != 0);
             u64 mida = 0, midb = 0;
-            // (destination, chunks) of every record of the batch, read back by the lanes that carry its bytes out of the stage
-            const u32 dsc = aux + CK_T2_AUX_BYTES + 1024u + 384u;
+            // the four records whose bytes this lane carries out of the stage (records 8 i + (lane >> 2), piece lane & 3): where
+            // the next piece goes (16-byte granules from a.out) and how many of its pieces are left
+            u32 og[4] = {0, 0, 0, 0}; int orem[4] = {0, 0, 0, 0};
             if (want_out) {
-                const u64 dp = reinterpret_cast<u64>(dst);
-                sts128(dsc + 16u * lane, make_uint4((u32)dp, (u32)(dp >> 32), nchunks, 0u));
-                __syncwarp();
+                const u32 gr = (u32)((dst - a.out) >> 4);
+#pragma unroll
+                for (u32 i = 0; i < 4; i++) {
+                    og[i] = __shfl_sync(CK_FULL, gr, 8 * i + (lane >> 2)) + (lane & 3u);
+                    orem[i] = (int)__shfl_sync(CK_FULL, nchunks, 8 * i + (lane >> 2)) - (int)(lane & 3u);
+                }
             }
             const u32 ost = aux + 80u * lane;                      // this lane's 64 bytes in the stage (stride 80: no conflicts)
             const u32 ord = aux + 80u * (lane >> 2) + 16u * (lane & 3u);
@@ -327,14 +331,12 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                 if (want_out) {                                                                                     \
                     sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);      \
                     __syncwarp();                                                                                   \
-                    const u32 c = 4 * s + (lane & 3u);                                                              \
-                    uint4 g[4], d[4];                                                                               \
-                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) {    /* records 8 i + (lane >> 2), piece lane & 3 */ \
-                        g[i] = lds128(ord + 640u * i);                                                              \
-                        d[i] = lds128(dsc + 16u * (8u * i + (lane >> 2)));                                          \
+                    uint4 g[4];                                                                                     \
+                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) g[i] = lds128(ord + 640u * i);                    \
+                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) {                                                 \
+                        if (orem[i] > 0) reinterpret_cast<uint4 *>(a.out)[og[i]] = g[i];                            \
+                        og[i] += 4; orem[i] -= 4;                                                                   \
                     }                                                                                               \
-                    _Pragma("unroll") for (u32 i = 0; i < 4; i++)                                                   \
-                        if (c < d[i].z) *reinterpret_cast<uint4 *>(((u64)d[i].y << 32 | d[i].x) + 64ull * s + 16u * (lane & 3u)) = g[i]; \
                     __syncwarp();                                                                                   \
                 }                                                                                                   \
                 if (++s >= rounds) break;                                                                           \
