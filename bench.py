@@ -53,9 +53,10 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=1,
                     help="multi-GPU uniq: sub-batches per rank, the exchange of one overlapping the kernels of the next "
                          "(measured at 2 GPUs: 2 or 4 sub-batches are slower than 1 -- smaller launches, more collectives)")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="uniq: run the table / exchange stage of a step on the same stream as its kernels (default: on a second "
-                         "stream, overlapping the canonicalisation of the next step, double-buffered outputs)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="uniq: run the table / exchange stage of a step on a second stream with double-buffered outputs, so that "
+                         "it overlaps the canonicalisation of the next step (measured: +3-7 % on config 2, but the table's random "
+                         "atomics can halve the speed of the latency-bound lane kernel on config 5, so it is off by default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline measurement")
@@ -293,7 +294,7 @@ def main():
     comm = torch.cuda.Stream(device=dev) if subs is not None else None
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
     if w["uniq"] and subs is None and raw_dev is None:
-        overlap = not args.no_overlap
+        overlap = args.overlap
         stage_stream = torch.cuda.Stream(device=dev) if overlap else None
         outs_sets = [outs, D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=True, aligned=True) if overlap else outs]
         first_sets = [first, torch.empty_like(first) if overlap else first]
@@ -330,7 +331,7 @@ def main():
             D.canon_packed2(ctx, batch, outs, ws, class_mask=w["mask"])
             return
         # uniq: kernels of step k on the current stream into output set k & 1; its table / exchange stage on `stage_stream`
-        # (the same stream with --no-overlap), so that it overlaps the kernels of step k + 1
+        # with --overlap (else the same stream), so that it overlaps the kernels of step k + 1
         i = pipe["k"] & 1
         pipe["k"] += 1
         o_i, f_i = outs_sets[i], first_sets[i]
