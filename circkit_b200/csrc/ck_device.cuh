@@ -34,6 +34,24 @@ struct Tables {
 };
 __constant__ Tables c_tab;   // single translation unit (ck_lib.cu): defined here
 
+// Per-CTA copy of the tables the byte-level lanes index with per-thread symbols.  A constant-bank load with a divergent
+// index is replayed once per distinct address (ncu r01 p17: LDC = 38 % of the stall samples of k_canon_warp<4>); the same
+// lookups in shared memory are one wavefront (16-entry tables: 4 words, 4 banks) or two (256-entry tables).  Kernels that
+// use the 4- or 8-bit lanes call stab_load() first; the 2-bit kernels never reference it.
+struct SharedTables {
+    u8 code4[256];
+    u8 comp[256];
+    u8 sym4[16];
+    u8 comp4[16];
+};
+__shared__ SharedTables s_tab;
+__device__ __forceinline__ void stab_load()
+{
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { s_tab.code4[i] = c_tab.code4[i]; s_tab.comp[i] = c_tab.comp[i]; }
+    if (threadIdx.x < 16) { s_tab.sym4[threadIdx.x] = c_tab.sym4[threadIdx.x]; s_tab.comp4[threadIdx.x] = c_tab.comp4[threadIdx.x]; }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ packed2 arena
 // 2-bit arena: A,C,G,T = 0..3, 16 bases per 32-bit unit, first base in the top bits, units in address order.  Record i
 // starts at 16-byte granule (offsets[i] >> 6) + 2 i (so every record can be streamed with aligned 128-bit loads), and
@@ -70,7 +88,7 @@ __device__ __forceinline__ u32 revcomp4_u32(u32 x)
     r = ((r >> 4) & 0x0f0f0f0fu) | ((r & 0x0f0f0f0fu) << 4);      // swap nibbles inside bytes
     u32 o = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) o |= (u32)c_tab.comp4[(r >> (4 * k)) & 15u] << (4 * k);
+    for (int k = 0; k < 8; k++) o |= (u32)s_tab.comp4[(r >> (4 * k)) & 15u] << (4 * k);
     return o;
 }
 __device__ __forceinline__ u32 revcomp8_u32(u32 x)
@@ -78,7 +96,7 @@ __device__ __forceinline__ u32 revcomp8_u32(u32 x)
     u32 r = __byte_perm(x, 0, 0x0123);
     u32 o = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) o |= (u32)c_tab.comp[(r >> (8 * k)) & 255u] << (8 * k);
+    for (int k = 0; k < 4; k++) o |= (u32)s_tab.comp[(r >> (8 * k)) & 255u] << (8 * k);
     return o;
 }
 template <int BITS> __device__ __forceinline__ u32 revcomp_unit(u32 x)

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) k_canon_warp(CanonArgs a)
 {
     extern __shared__ u32 smem[];
     typedef Grp<false> G;
+    if (BITS != 2) stab_load();
     const u32 wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     u32 *Xf = smem + (size_t)wid * 2 * a.smem_units, *Xr = Xf + a.smem_units;
     const u32 gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(1024) k_canon_cta(CanonArgs a)
     __shared__ u32 red[40];
     __shared__ u64 hbuf[32 * 8];
     typedef Grp<true> G;
+    if (BITS != 2) stab_load();
     u32 *Xf = XGLOBAL ? a.xglobal + (size_t)blockIdx.x * 2 * a.smem_units : smem;
     u32 *Xr = Xf + a.smem_units;
     u32 *scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
@@ -198,77 +200,231 @@ __global__ void k_canon_empty(CanonArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_prepare: one warp per raw record.
+// k_prepare: one warp per raw record, 512 raw bytes per warp iteration (16 per lane, two aligned 128-bit loads).
 //   flags bit0 (normalise): needletail::sequence::normalize(seq, false) -- src/canonicalize.rs:24-27
 //                           (whitespace dropped, acgt -> upper, t/u/U -> T, ./~ -> -, anything else -> N)
 //   otherwise             : library semantics, bytes are taken as they are (lib/src/canonicalize.rs:54)
 // Writes lens[i], lane[i] (2, 4 or 8 bits per symbol) and the record in that lane's format:
 //   lane 2 -> packed2 at word p2_word(offsets[i], i);   lanes 4/8 -> normalised bytes at offsets[i].
+// Pass 1 classifies and counts through a 256-entry shared-memory table (mapped byte | keep | not-ACGT | not-16-symbol);
+// pass 2 writes.  A 2-bit record without dropped bytes is packed straight from the raw bytes (the 2-bit code only reads
+// bits 1-2 of a byte, which a/A, c/C, g/G, t/T/u/U share); everything else is compacted through a per-warp stage that is
+// laid out congruent to the destination (mod 16 symbols / bytes), so that it leaves as aligned 128-bit pieces.
 struct PrepareArgs {
     const u8 *raw; const u64 *offsets; u32 n_records; u32 flags;
     u64 *packed2; u8 *bytes; u32 *lens; u8 *lane;
 };
 __device__ __forceinline__ u32 code2_of(u32 b) { return ((b >> 1) & 3u) ^ ((b >> 2) & 1u); }   // A,C,G,T -> 0..3
 
+// 16 raw bytes starting `sh` bytes into the aligned word *w; each of the two aligned words is read only if it holds a byte
+// of the record (an aligned word that does cannot leave the mapped page the record is in)
+__device__ __forceinline__ uint4 prep_load16(const uint4 *w, u32 sh, bool second, bool first = true)
+{
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (first) a = __ldg(w);
+    if (second) b = __ldg(w + 1);
+    const u32 bs = 8u * (sh & 3u);
+    uint4 q;
+    switch (sh >> 2) {                                   // warp-uniform (one record per warp)
+    case 0: q.x = __funnelshift_r(a.x, a.y, bs); q.y = __funnelshift_r(a.y, a.z, bs); q.z = __funnelshift_r(a.z, a.w, bs); q.w = __funnelshift_r(a.w, b.x, bs); break;
+    case 1: q.x = __funnelshift_r(a.y, a.z, bs); q.y = __funnelshift_r(a.z, a.w, bs); q.z = __funnelshift_r(a.w, b.x, bs); q.w = __funnelshift_r(b.x, b.y, bs); break;
+    case 2: q.x = __funnelshift_r(a.z, a.w, bs); q.y = __funnelshift_r(a.w, b.x, bs); q.z = __funnelshift_r(b.x, b.y, bs); q.w = __funnelshift_r(b.y, b.z, bs); break;
+    default: q.x = __funnelshift_r(a.w, b.x, bs); q.y = __funnelshift_r(b.x, b.y, bs); q.z = __funnelshift_r(b.y, b.z, bs); q.w = __funnelshift_r(b.z, b.w, bs); break;
+    }
+    return q;
+}
+// four A/C/G/T bytes (first one in the low bits) -> their 2-bit codes in the top byte, first base in the top bits
+__device__ __forceinline__ u32 prep_pack4(u32 x)
+{
+    const u32 c = ((x >> 1) & 0x03030303u) ^ ((x >> 2) & 0x01010101u);
+    return c * 0x40100401u;      // byte k lands at bits 30 - 2k; the cross terms stay below bit 24 and never carry
+}
+__device__ __forceinline__ u32 prep_pack16(uint4 q)
+{
+    const u32 lo = __byte_perm(prep_pack4(q.w), prep_pack4(q.z), 0x0073);
+    const u32 hi = __byte_perm(prep_pack4(q.y), prep_pack4(q.x), 0x0073);
+    return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ u32 prep_byte(const uint4 &q, int k)
+{
+    const u32 w = (k >> 2) == 0 ? q.x : (k >> 2) == 1 ? q.y : (k >> 2) == 2 ? q.z : q.w;
+    return (w >> (8 * (k & 3))) & 0xffu;
+}
+
+// table lookups for 16 raw bytes, of which bytes [lo, hi) belong to the record: mapped bytes (0 = dropped), OR of the
+// table flags, bit mask of the kept bytes.  Bytes outside [lo, hi) are looked up as 'A' (kept, no flag).
+__device__ __forceinline__ void prep_lookup(const u16 *tab, uint4 q, u32 lo, u32 hi, uint4 &m, u32 &fl, u32 &keep)
+{
+    u32 w[4] = {q.x, q.y, q.z, q.w};
+    const u32 valid = (hi >= 16 ? 0xffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // nibble of `valid` -> byte mask (bit k of the nibble lands on bit 8 k, times 0xff); no carries anywhere
+        const u32 vm = ((((valid >> (4 * i)) & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+        w[i] = (w[i] & vm) | (0x41414141u & ~vm);
+    }
+    const char *tb = reinterpret_cast<const char *>(tab);
+    u32 all = 0x100u, any = 0, mm[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 e0 = *reinterpret_cast<const u16 *>(tb + ((w[i] << 1) & 0x1feu));
+        const u32 e1 = *reinterpret_cast<const u16 *>(tb + ((w[i] >> 7) & 0x1feu));
+        const u32 e2 = *reinterpret_cast<const u16 *>(tb + ((w[i] >> 15) & 0x1feu));
+        const u32 e3 = *reinterpret_cast<const u16 *>(tb + ((w[i] >> 23) & 0x1feu));
+        all &= e0 & e1 & e2 & e3;
+        any |= e0 | e1 | e2 | e3;
+        mm[i] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+    }
+    m = make_uint4(mm[0], mm[1], mm[2], mm[3]);
+    fl = any;
+    keep = valid;
+    if (!all) {                                          // some byte is dropped (normalise mode: its mapped byte is 0)
+        u32 nz = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32 t = ((mm[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | mm[i];
+            nz |= ((((t >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+        }
+        keep = valid & nz;
+    }
+}
+
+#define CK_PREP_STAGE 560u     // 16 carried bytes + 512 + slack, per warp
+
 __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
 {
-    const u32 lane = lane_id();
-    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    __shared__ u16 tab[256];
+    __shared__ __align__(16) u8 stage_all[8][CK_PREP_STAGE];
     const bool norm = a.flags & 1u;
+    for (u32 b = threadIdx.x; b < 256; b += blockDim.x) {
+        const u32 m = norm ? (u32)c_tab.norm[b] : b;
+        const bool keep = norm ? m != 0 : true;
+        const bool acgt = (m == 'A') | (m == 'C') | (m == 'G') | (m == 'T');
+        u32 e = 0;
+        if (keep) e = m | 0x100u | (acgt ? 0u : 0x200u) | ((!acgt && c_tab.code4[m] == 0xffu) ? 0x400u : 0u);
+        tab[b] = (u16)e;
+    }
+    __syncthreads();
+    const u32 lane = lane_id();
+    u8 *stage = stage_all[threadIdx.x >> 5];
+    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 rec = gw; rec < a.n_records; rec += nw) {
         const u64 off = a.offsets[rec];
         const u32 rawlen = (u32)(a.offsets[rec + 1] - off);
         const u8 *src = a.raw + off;
-        // pass 1: normalised length and alphabet class
-        u32 cnt = 0, cls = 0;
-        for (u32 base = 0; base < rawlen; base += 32) {
-            u32 t = base + lane;
-            u32 m = 0;
-            if (t < rawlen) { u32 b = __ldg(src + t); m = norm ? (u32)c_tab.norm[b] : (b | 0x100u); }
-            if (m) {
-                u32 b = m & 0xffu;
-                bool acgt = (b == 'A') | (b == 'C') | (b == 'G') | (b == 'T');
-                cls |= acgt ? 0u : (c_tab.code4[b] != 0xffu ? 1u : 3u);
-            }
-            cnt += __popc(__ballot_sync(CK_FULL, m != 0));
-        }
-        cls = __reduce_or_sync(CK_FULL, cls);
-        const u32 lanebits = cls == 0 ? 2u : (cls == 1 ? 4u : 8u);
-        if (lane == 0) { a.lens[rec] = cnt; a.lane[rec] = (u8)lanebits; }
-        // pass 2: write in the lane's format
-        u64 *dstw = a.packed2 + p2_word(off, rec);
         u8 *dstb = a.bytes + off;
-        u32 done = 0;                 // normalised symbols written so far
-        u32 acc_hi = 0, acc_lo = 0;   // word under construction (uniform across the warp)
-        for (u32 base = 0; base < rawlen; base += 32) {
-            u32 t = base + lane;
-            u32 m = 0;
-            if (t < rawlen) { u32 b = __ldg(src + t); m = norm ? (u32)c_tab.norm[b] : (b | 0x100u); }
-            const u32 keep = __ballot_sync(CK_FULL, m != 0);
-            const u32 idx = done + __popc(keep & ((1u << lane) - 1u));
-            if (lanebits != 2) {
-                if (m) dstb[idx] = (u8)m;
-            } else {
-                // symbols of this chunk fall into word A = done >> 5 and possibly A + 1
-                const u32 A = done >> 5;
-                u32 c_hi0 = 0, c_lo0 = 0, c_hi1 = 0, c_lo1 = 0;
-                if (m) {
-                    u32 code = code2_of(m & 0xffu), sh = 62 - 2 * (idx & 31u);
-                    u32 hi = sh >= 32 ? code << (sh - 32) : 0u, lo = sh < 32 ? code << sh : 0u;
-                    if ((idx >> 5) == A) { c_hi0 = hi; c_lo0 = lo; } else { c_hi1 = hi; c_lo1 = lo; }
-                }
-                acc_hi |= __reduce_or_sync(CK_FULL, c_hi0);
-                acc_lo |= __reduce_or_sync(CK_FULL, c_lo0);
-                const u32 ndone = done + __popc(keep);
-                if ((ndone >> 5) != A) {          // word A is complete
-                    if (lane == 0) dstw[A] = ((u64)acc_lo << 32) | acc_hi;   // unit of bases 0-15 at the lower address
-                    acc_hi = __reduce_or_sync(CK_FULL, c_hi1);
-                    acc_lo = __reduce_or_sync(CK_FULL, c_lo1);
+        // pass 1 walks the record in pieces congruent to the byte destination: piece w = destination bytes
+        // [gbase + 16 w, + 16), i.e. record positions [16 w - A, 16 w - A + 16)
+        const u32 A = (u32)((size_t)dstb & 15u);
+        u8 *gbase = dstb - A;
+        const u8 *srcA = src - A;
+        const u32 shA = (u32)((size_t)srcA & 15u);
+        const uint4 *srcA16 = reinterpret_cast<const uint4 *>(srcA - shA);
+        const u32 spanA = A + rawlen;                    // pieces cover [0, spanA) in these coordinates, record at [A, spanA)
+        u32 fl = 0, cnt = 0;
+        uint4 m1 = make_uint4(0, 0, 0, 0);
+        for (u32 base = 0; base < spanA && rawlen; base += 512) {
+            const u32 p = base + 16 * lane;
+            if (p < spanA) {
+                const u32 lo = p < A ? A - p : 0u, hi = min(16u, spanA - p);
+                const uint4 *w0 = srcA16 + (p >> 4);
+                const uint4 q = prep_load16(w0, shA, p + 16 < spanA + shA, p + 16 > A + shA);
+                u32 f, keep;
+                prep_lookup(tab, q, lo, hi, m1, f, keep);
+                fl |= f; cnt += __popc(keep);
+            }
+        }
+        cnt = __reduce_add_sync(CK_FULL, cnt);
+        fl = __reduce_or_sync(CK_FULL, fl);
+        const u32 lanebits = (fl & 0x400u) ? 8u : (fl & 0x200u) ? 4u : 2u;
+        if (lane == 0) { a.lens[rec] = cnt; a.lane[rec] = (u8)lanebits; }
+        if (rawlen == 0) continue;
+        // pass 2: write in the lane's format
+        const u32 sh = (u32)((size_t)src & 15u);
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(src - sh);
+        const u32 span = sh + rawlen;                   // bytes from *src16 to the end of the record
+        u32 *dst32 = reinterpret_cast<u32 *>(a.packed2 + p2_word(off, rec));     // 16-base units in address order
+        if (cnt == rawlen && lanebits == 2) {            // nothing dropped: pack straight from the raw bytes
+            for (u32 base = 0; base < rawlen; base += 512) {
+                const u32 p = base + 16 * lane;
+                if (p < rawlen) {
+                    const u32 v = min(16u, rawlen - p);
+                    u32 unit = prep_pack16(prep_load16(src16 + (p >> 4), sh, p + 16 < span));
+                    if (v < 16) unit &= ~(0xffffffffu >> (2 * v));
+                    dst32[p >> 4] = unit;
                 }
             }
-            done += __popc(keep);
+            continue;
         }
-        if (lanebits == 2 && (done & 31u) && lane == 0) dstw[done >> 5] = ((u64)acc_lo << 32) | acc_hi;
+        if (cnt == rawlen && spanA <= 512) {             // nothing dropped, one piece per lane: the mapped bytes are at hand
+            const u32 p = 16 * lane;
+            if (p < spanA) {
+                const u32 lo = p < A ? A - p : 0u, hi = min(16u, spanA - p);
+                if (hi - lo == 16) *reinterpret_cast<uint4 *>(gbase + p) = m1;
+                else {                                   // first / last piece: whole 32-bit words, then single bytes
+                    const u32 valid = (hi >= 16 ? 0xffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    const u32 w[4] = {m1.x, m1.y, m1.z, m1.w};
+                    u8 *g = gbase + p;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const u32 nib = (valid >> (4 * i)) & 15u;
+                        if (nib == 15u) *reinterpret_cast<u32 *>(g + 4 * i) = w[i];
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) if ((nib >> j) & 1u) g[4 * i + j] = (u8)(w[i] >> (8 * j));
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        // general path: compact the kept bytes through the stage, laid out congruent to the destination
+        u32 S = lanebits == 2 ? 0u : A;                  // stage[S ..) <-> next symbol to place
+        u32 done = 0;                                    // 2-bit: full units stored; bytes: bytes stored
+        for (u32 base = 0; base < rawlen; base += 512) {
+            const u32 p = base + 16 * lane;
+            uint4 m = make_uint4(0, 0, 0, 0);
+            u32 mask = 0;
+            if (p < rawlen) {
+                u32 f;
+                prep_lookup(tab, prep_load16(src16 + (p >> 4), sh, p + 16 < span), 0u, min(16u, rawlen - p), m, f, mask);
+            }
+            // exclusive scan of the kept counts
+            const u32 kc = __popc(mask);
+            u32 incl = kc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(CK_FULL, incl, d); if (lane >= (u32)d) incl += t; }
+            const u32 T = __shfl_sync(CK_FULL, incl, 31);
+            u32 idx = S + incl - kc;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if ((mask >> k) & 1u) stage[idx++] = (u8)prep_byte(m, k);
+            __syncwarp();
+            const u32 fill = S + T;                                  // stage[0, fill) is valid
+            if (lanebits == 2) {
+                const u32 U = fill >> 4;
+                for (u32 j = lane; j < U; j += 32) dst32[done + j] = prep_pack16(*reinterpret_cast<const uint4 *>(stage + 16 * j));
+                const u32 r = fill & 15u;
+                u8 c = 0;
+                if (lane < r) c = stage[16 * U + lane];
+                __syncwarp();
+                if (lane < r) stage[lane] = c;
+                done += U; S = r;
+            } else {
+                u8 *g = dstb + done - S;                             // 16-byte aligned, congruent to the stage
+                for (u32 w = lane; 16 * w < fill; w += 32) {
+                    const u32 lo = max(16 * w, S), hi = min(16 * w + 16, fill);
+                    if (hi - lo == 16) *reinterpret_cast<uint4 *>(g + 16 * w) = *reinterpret_cast<const uint4 *>(stage + 16 * w);
+                    else for (u32 i = lo; i < hi; i++) g[i] = stage[i];
+                }
+                done += T; S = (u32)((size_t)(dstb + done) & 15u);
+            }
+        }
+        __syncwarp();
+        if (lanebits == 2 && S && lane == 0)
+            dst32[done] = prep_pack16(*reinterpret_cast<const uint4 *>(stage)) & ~(0xffffffffu >> (2 * S));
+        __syncwarp();
     }
 }
 

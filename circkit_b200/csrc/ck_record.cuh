@@ -79,7 +79,7 @@ template <int BITS> __device__ __forceinline__ u32 sym_global(const RecordIn &r,
 {
     if (BITS == 2) return (reinterpret_cast<const u32 *>(r.packed2)[t >> 4] >> (30 - 2 * (t & 15))) & 3u;
     u32 b = r.bytes[t];
-    return BITS == 4 ? (u32)c_tab.code4[b] : b;
+    return BITS == 4 ? (u32)s_tab.code4[b] : b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -109,7 +109,7 @@ __device__ __forceinline__ void stage_record(const RecordIn &r, u32 *Xf, u32 *Xr
             for (int i = 0; i < S; i++) {
                 u32 t = j * S + i;
                 u32 c = 0;
-                if (t < n) { u32 b = __ldg(r.bytes + t); c = BITS == 4 ? (u32)c_tab.code4[b] : b; }
+                if (t < n) { u32 b = __ldg(r.bytes + t); c = BITS == 4 ? (u32)s_tab.code4[b] : b; }
                 v = (v << BITS) | c;
             }
             Xf[j] = v;
@@ -355,7 +355,7 @@ template <int BITS> __device__ __forceinline__ u64 ascii8(const u32 *X, u32 n, u
         u32 w = window32<4>(X, q);
         u64 o = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) o |= (u64)c_tab.sym4[(w >> (28 - 4 * k)) & 15u] << (8 * k);
+        for (int k = 0; k < 8; k++) o |= (u64)s_tab.sym4[(w >> (28 - 4 * k)) & 15u] << (8 * k);
         return o;
     } else {
         u32 a = window32<8>(X, q), b = window32<8>(X, q + 4);     // q + 4 stays inside the extension

@@ -200,3 +200,44 @@ def test_owner_partition_matches_owner_of(env, world):
     o_sorted = owner_of(hs, world).cpu().numpy()
     for r in range(world):
         assert (o_sorted[starts[r]: starts[r + 1]] == r).all()
+
+
+@pytest.mark.parametrize("normalize", [True, False], ids=["cli-semantics", "lib-semantics"])
+@pytest.mark.parametrize("skew", [0, 1, 7, 13])
+def test_prepare_any_alignment_and_every_path(env, normalize, skew):
+    """k_prepare (normalise + classify + pack) on raw bytes whose base address is not 16-byte aligned: records with and
+    without dropped bytes, one and many 512-byte pieces, all three symbol lanes -- lengths and canonical forms against
+    the oracle (needletail normalisation rules: src/canonicalize.rs:24)."""
+    ctx, D, torch = env
+    rng = np.random.default_rng(100 + skew + (50 if normalize else 0))
+    alphabets = [b"ACGT", b"ACGTacgtuU", b"ACGTN-", b"ACGTNRYKMSWBDHV-", b"ACGTacgtNnUuRYx*.~", b"ACGT\n", b"ACGTNn \t\r\n"]
+    seqs = []
+    for n in list(range(0, 40)) + [495, 496, 497, 511, 512, 513, 527, 528, 529, 1023, 1024, 1025, 1500, 4000]:
+        for alpha in alphabets:
+            seqs.append(bytes(rng.choice(np.frombuffer(alpha, np.uint8), n).astype(np.uint8)))
+    for _ in range(600):
+        alpha = alphabets[int(rng.integers(len(alphabets)))]
+        seqs.append(bytes(rng.choice(np.frombuffer(alpha, np.uint8), int(rng.integers(1, 900))).astype(np.uint8)))
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64); np.cumsum(lens, out=off[1:])
+    arena = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    n, total = len(seqs), int(off[-1])
+    dev = torch.device("cuda", ctx.device)
+    buf = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    raw = buf[skew: skew + total]
+    raw.copy_(torch.from_numpy(arena.copy()))
+    offsets = torch.from_numpy(off).to(dev)
+    ws = D.Workspace(ctx, n, total)
+    outs = D.CanonOutputs(n, total, dev, want_bytes=True, want_hash=True, aligned=True)
+    lens_out = torch.empty(n, dtype=torch.int32, device=dev)
+    D.canon_bytes(ctx, raw, offsets, n, total, outs, lens_out, ws, normalize=normalize)
+    D.check(ctx, ws)
+    want = oracle.canonicalize_batch(arena, off.astype(np.uint64), normalize=normalize, threads=8)
+    got_len = lens_out.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got_len, want["lens"].astype(np.int64))
+    assert np.array_equal(outs.hash.cpu().numpy().astype(np.uint64), want["hash"])
+    out = outs.out.cpu().numpy()
+    starts = 32 * ((off[:-1] >> 5) + np.arange(n))
+    for i in range(n):
+        a, ln = int(off[i]), int(got_len[i])                    # the oracle keeps record i at its raw offset
+        assert out[starts[i]: starts[i] + ln].tobytes() == want["out"][a: a + ln].tobytes(), (i, seqs[i][:60])
