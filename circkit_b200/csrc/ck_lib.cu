@@ -32,9 +32,9 @@ const ClsCfg kCls[CLS_COUNT] = {
     {2, false, 256, 6},   // CLS_W2M
     {2, true, 512, 4},    // CLS_C2A
     {2, true, 1024, 1},   // CLS_C2B
-    {4, false, 256, 8},   // CLS_W4
+    {4, false, 256, 32},  // CLS_W4
     {4, true, 1024, 1},   // CLS_C4
-    {8, false, 256, 8},   // CLS_W8
+    {8, false, 256, 32},  // CLS_W8
     {8, true, 1024, 1},   // CLS_C8
     {0, true, 0, 0},      // CLS_HUGE (handled separately)
     {0, false, 256, 1},   // CLS_EMPTY
@@ -357,7 +357,7 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
     PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
-    k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
+    k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
     k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records);
     ctx->launches += 2;
     CanonIO io{};
@@ -575,7 +575,7 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     if (total) CK_LB(cudaMemcpy(d_raw, bytes, total, cudaMemcpyHostToDevice));
     if (e == cudaSuccess) {
         PrepareArgs pa{d_raw, d_off, n_records, 0u, d_p2, d_norm, d_len, d_lane};
-        k_prepare<<<ctx->num_sms * 8, 256>>>(pa);
+        k_prepare<<<ctx->num_sms * 32, 256>>>(pa);
         k_extend_packed2<<<(n_records + 255) / 256, 256>>>(d_p2, d_off, d_len, d_lane, n_records);
         ctx->launches += 2;
         CanonIO io{};
@@ -666,7 +666,7 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     u8 *lane = w;
     cudaStream_t st = (cudaStream_t)stream;
     PrepareArgs pa{bytes, U(offsets), n_records, flags & CK_F_NORMALIZE, p2, norm, out_len, lane};
-    k_prepare<<<ctx->num_sms * 8, 256, 0, st>>>(pa);
+    k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
     k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records);
     ctx->launches += 2;
     CanonIO io{};
