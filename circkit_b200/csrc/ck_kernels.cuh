@@ -440,6 +440,9 @@ struct ClassifyArgs {
     u32 *counts;       // 16 class counters (zeroed by the caller), followed by 16 run starts (k_list_starts)
     u32 direct_mask;   // != 0: no keys are written (the classes of the mask run over all records directly);
                        // records of any other class are counted in counts[CLS_HUGE] = "left unprocessed"
+    u32 window_shift;  // < 32: the lane-kernel classes are keyed (index >> window_shift, length bin) instead of (class, length bin):
+    u32 top_bit;       //       the records a warp walks together then come from one window of the arenas, which L2 can hold;
+                       //       every other class gets bit `top_bit` set and keeps (class, bin), i.e. sorts behind them
 };
 __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
 {
@@ -473,7 +476,13 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
             // config 2: 1/32 octave 9.7 ms, 1/8 octave 8.6 ms, 1/4 octave 8.4 ms)
             const u32 msb = 31u - __clz(n | 1u);
             const u32 bin = (msb << 5) | ((((n << (31u - msb)) >> 29) & 3u) << 3);
-            a.keys[i] = (cls_rank(cls) << 10) | bin; a.vals[i] = i;
+            u32 key = (cls_rank(cls) << 10) | bin;
+            if (a.window_shift < 32u) {
+                const bool lane_cls = cls == CLS_W2S || cls == CLS_W2M || cls == CLS_W2L || cls == CLS_W2X;
+                const u32 q = (msb << 2) | (((n << (31u - msb)) >> 29) & 3u);            // quarter octaves; n <= 8192: q <= 52
+                key = lane_cls ? (((i >> a.window_shift) << 5) | (q > 28u ? q - 28u : 0u)) : (key | (1u << a.top_bit));
+            }
+            a.keys[i] = key; a.vals[i] = i;
         }
         // warp-aggregated counting: one shared-memory atomic per (warp, class present)
         u32 todo = __ballot_sync(CK_FULL, cls >= 0);

@@ -226,7 +226,20 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     const u64 stride = ((u64)io.n + 4) & ~3ull;                // u32 elements per sort buffer
     u32 *k0 = io.lists, *k1 = k0 + stride, *v0 = k1 + stride, *v1 = v0 + stride;
     if (io.lists_bytes < 16 * stride) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
-    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u};
+    // both strands, aligned bytes or none: the lane-per-record streaming kernel; everything else (forward-only library
+    // calls, output at the input's offsets): the run-time-option warp-per-record kernel
+    const bool fastv = io.packed2 && !(io.mode & 1u) && (!io.out || (io.mode & 2u)) && io.out_start && io.out_strand;
+    u32 window_shift = 32, top_bit = 13;
+    if (fastv && only < 0) {
+        // windows of 64 K records (config 2, lane kernel: none 6.30 ms, 1 K 5.97, 4 K 5.89, 16 K 5.88, 64 K 5.86, 256 K 5.96; 1/8-octave bins inside the windows 5.89;
+        // DRAM reads of the launch 13.1 -> 11.0 GB, of its scan pass alone 7.4 -> 5.1 GB: profiles/r01_j_traffic.txt)
+        window_shift = 16;
+        u32 wbits = 0;
+        while ((((u64)io.n - 1) >> window_shift) >> wbits) wbits++;
+        top_bit = std::max(14u, 5u + wbits);
+    }
+    const int sort_bits = (int)top_bit + 1;
+    ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u, window_shift, top_bit};
     k_classify<<<std::min<u32>((io.n + 255) / 256, 16u * (u32)ctx->num_sms), 256, 0, st>>>(ca);
     ctx->launches++;
     const u32 *sorted = nullptr;
@@ -236,17 +249,14 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         cub::DoubleBuffer<u32> keys(k0, k1), vals(v0, v1);
         void *tmp = v1 + stride;
         size_t tmp_bytes = (size_t)(io.lists_bytes - 16 * stride), need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)io.n, 0, 14, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)io.n, 0, sort_bits, st);
         if (need > tmp_bytes) return fail(ctx, CK_ERR_ARG, "sort workspace too small");
-        CK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, (int)io.n, 0, 14, st));
+        CK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, (int)io.n, 0, sort_bits, st));
         sorted = vals.Current();
         retry = vals.Alternate();
         k_list_starts<<<1, 32, 0, st>>>(io.counts);
         ctx->launches += 2;
     }
-    // both strands, aligned bytes or none: the lane-per-record streaming kernel; everything else (forward-only library
-    // calls, output at the input's offsets): the run-time-option warp-per-record kernel
-    const bool fastv = io.packed2 && !(io.mode & 1u) && (!io.out || (io.mode & 2u)) && io.out_start && io.out_strand;
     const u32 lane_classes = (1u << CLS_W2S) | (1u << CLS_W2M) | (1u << CLS_W2L) | (1u << CLS_W2X);
     auto timed = [&](int slot, cudaEvent_t &e0, cudaEvent_t &e1, bool begin) -> cudaError_t {
         if (!ctx->timing) return cudaSuccess;
