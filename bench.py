@@ -57,6 +57,11 @@ def parse_args():
                     help="uniq: run the table / exchange stage of a step on a second stream with double-buffered outputs, so that "
                          "it overlaps the canonicalisation of the next step (measured: +3-7 % on config 2, but the table's random "
                          "atomics can halve the speed of the latency-bound lane kernel on config 5, so it is off by default)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "padded", "exact"],
+                    help="multi-GPU uniq, how (hash, index) pairs reach their owner: peer = stored straight into the owner's buffer by "
+                         "the partition kernel over NVLink (fixed-capacity buckets, device-side barriers, no collective); padded = "
+                         "the same buckets through one equal-split NCCL all-to-all each way; exact = per-owner counts exchanged first "
+                         "(two host synchronisations per step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline measurement")
@@ -177,7 +182,10 @@ def main():
               "records_per_gpu": w["records"], "length_law": ["uniform", "log-uniform"][w["kind"]],
               "length_range": [w["lo"], w["hi"]], "duplicate_fraction": w["dup"] / 1000.0,
               "l2_policy": "inputs larger than L2 (packed arena + ASCII output per step >> 126 MB)",
-              "sharding": "contiguous input-index ranges per GPU; uniq keys exchanged by hash range (all-to-all)"}
+              "sharding": "contiguous input-index ranges per GPU; uniq keys owned by hash range, exchange: " +
+                          {"peer": "partition / query kernels store into the peers' buffers over NVLink, device-side barriers",
+                           "padded": "fixed-capacity buckets, equal-split NCCL all-to-all",
+                           "exact": "counts, then NCCL all-to-all"}[args.exchange]}
 
     # ---------------- reference arm: the CPU path, rank 0 only
     if args.impl == "reference":
@@ -291,6 +299,21 @@ def main():
             table.first(slots, m, out)
             return out[:m]
 
+        def first_pairs_fn(pairs):                  # owner side of the padded exchange: insert, then query, padding skipped
+            m = pairs.shape[0]
+            key = ("pairs", m)
+            if key not in slot_cache:
+                slot_cache[key] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
+                                   torch.empty(max(m, 1), dtype=torch.int64, device=dev))
+            slots, out = slot_cache[key]
+            table.insert_pairs(pairs, m, slots)
+            table.first(slots, m, out)
+            return out[:m]
+
+    padded = {"on": world > 1 and args.exchange != "exact" and w["uniq"], "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
+              "peer": None}
+    if padded["on"] and args.exchange == "peer" and subs is None:
+        padded["peer"] = D.PeerExchange(ctx, R, world, rank, dev)
     comm = torch.cuda.Stream(device=dev) if subs is not None else None
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
     if w["uniq"] and subs is None and raw_dev is None:
@@ -345,6 +368,15 @@ def main():
             table.clear()
             if world == 1:
                 f_i.copy_(first_fn(o_i.hash[:R], None))
+            elif padded["on"]:
+                # fixed-capacity buckets: no counts to exchange, no host synchronisation in the step; an overflowing bucket is
+                # flagged on the device and checked after the steps have been queued
+                if padded["peer"] is not None:      # partition and query kernels store straight into the peers' buffers
+                    state = padded["peer"].first_index(o_i.hash[:R], base_index, table, f_i)
+                else:                               # the same buckets through one equal-split all-to-all each way
+                    f, state = X.exchange_first_index_padded(o_i.hash[:R], base_index, first_pairs_fn, padded_fn=partitioner.padded)
+                    f_i.copy_(f)
+                padded["overflow"].add_(state[world: world + 1])
             else:
                 pend = X.exchange_send(o_i.hash[:R], base_index, partitioner, insert_pairs_fn)
                 f_i.copy_(X.exchange_finish(pend, first_query_fn))
@@ -370,6 +402,17 @@ def main():
     drain()
     sync_all()
     check_all()
+    if padded["on"]:
+        ov = padded["overflow"].clone().to(torch.int64)
+        dist.all_reduce(ov, op=dist.ReduceOp.MAX)
+        if int(ov.item()):                              # a bucket overflowed somewhere: every rank takes the exact path
+            padded["on"] = False
+            padded["peer"] = None
+            padded["overflow"].zero_()
+            for _ in range(args.warmup):
+                step()
+            drain()
+            sync_all()
     ctx._lib.ck_kernel_timing(ctx.handle, 1)
     D.kernel_times(ctx)
     launches0 = ctx.launch_count()
@@ -382,6 +425,8 @@ def main():
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    if padded["on"] and int(padded["overflow"].item()):
+        raise RuntimeError("padded exchange overflowed inside the timed steps although the warm-up steps on the same data did not")
     if pipe is not None:
         first = first_sets[(pipe["k"] - 1) & 1]             # result of the last step
     clocks = sampler.stop(t_window0, time.time())

@@ -53,6 +53,10 @@ SIGNATURES = {
     "ck_dev_table_first": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "ck_dev_owner_partition": (_i, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
     "ck_dev_table_insert_pairs": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "ck_dev_owner_partition_padded": (_i, [_vp, _vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp, _vp]),
+    "ck_dev_owner_scatter_peers": (_i, [_vp, _vp, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "ck_dev_table_first_peers": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp]),
+    "ck_dev_gather_first": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
     "ck_launch_count": (_u64, [_vp]),
     "ck_kernel_timing": (_i, [_vp, _i]),
     "ck_kernel_times": (_i, [_vp, _vp, _vp, _u32]),

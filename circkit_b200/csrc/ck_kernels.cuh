@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(256) k_table_insert(TableArgs a)
     if (i >= a.n) return;
     const u64 key = a.hash[(size_t)i * a.stride];
     const u64 idx = a.index ? a.index[(size_t)i * a.stride] : a.base_index + i;
+    if (idx == ~0ULL) { a.slot_of[i] = ~0ULL - 1; return; }     // padding of a fixed-capacity exchange bucket (k_owner_pad)
     if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); a.slot_of[i] = ~0ULL; return; }
     u64 s = table_home(key, a.mask);
     for (u64 probes = 0; probes <= a.mask; probes++) {
@@ -644,6 +645,126 @@ __global__ void __launch_bounds__(256) k_owner_scatter(OwnerArgs a)
         const u32 p = basep[o] + atomicAdd(cnt + o, 1u);
         reinterpret_cast<ulonglong2 *>(a.send_pairs)[p] = make_ulonglong2(h, a.base_index + i);
         a.pos[i] = p;
+    }
+}
+
+
+// The same partition into FIXED-capacity buckets (bucket o = send_pairs[o * cap, (o + 1) * cap)): one pass, no counts to
+// exchange and nothing for the host to wait for -- the buckets go out as an equal-split all-to-all.  XXH3 keys spread
+// evenly, so cap = n / world plus a few standard deviations wastes well under 1 % of the volume; a bucket that would
+// overflow (a heavily duplicated key set) raises *overflow and the caller repeats the batch through the exact path.
+struct OwnerPadArgs {
+    const u64 *hash; u32 n; u32 world; u64 base_index; u32 cap;
+    u32 *cursors;      // [world] records placed per bucket so far (zeroed by the caller), [world] = overflow flag
+    u64 *send_pairs; u32 *pos;
+};
+__global__ void __launch_bounds__(256) k_owner_scatter_padded(OwnerPadArgs a)
+{
+    __shared__ u32 cnt[32], basep[32];
+    const u32 per = (a.n + gridDim.x - 1) / gridDim.x;
+    const u32 lo = min(a.n, blockIdx.x * per), hi = min(a.n, lo + per);
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(cnt + owner_of_hash(a.hash[i], a.world), 1u);
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        basep[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(a.cursors + threadIdx.x, cnt[threadIdx.x]) : 0u;
+        if (basep[threadIdx.x] + cnt[threadIdx.x] > a.cap) a.cursors[a.world] = 1u;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const u64 h = a.hash[i];
+        const u32 o = owner_of_hash(h, a.world);
+        const u32 k = basep[o] + atomicAdd(cnt + o, 1u);
+        u32 p = 0xffffffffu;
+        if (k < a.cap) {
+            p = o * a.cap + k;
+            reinterpret_cast<ulonglong2 *>(a.send_pairs)[p] = make_ulonglong2(h, a.base_index + i);
+        }
+        a.pos[i] = p;
+    }
+}
+// the unused tail of every bucket: index ~0 = "no record" (k_table_insert skips it)
+__global__ void __launch_bounds__(256) k_owner_pad(OwnerPadArgs a)
+{
+    const u32 o = blockIdx.y;
+    const u32 used = min(a.cursors[o], a.cap);
+    for (u32 k = used + blockIdx.x * blockDim.x + threadIdx.x; k < a.cap; k += gridDim.x * blockDim.x)
+        reinterpret_cast<ulonglong2 *>(a.send_pairs)[(size_t)o * a.cap + k] = make_ulonglong2(0ULL, ~0ULL);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The exchange fused into the two kernels around it, over peer-mapped memory (NVLink / NVSwitch loads and stores):
+//   k_owner_scatter_peers  the partition writes every (hash, index) pair straight into its owner's receive buffer
+//                          (region `rank` of it, same fixed capacity as above) and pads the tail of that region;
+//   k_table_first_peers    the owner's query writes every answer straight into the asking rank's return buffer, in the
+//                          order the pairs were sent, so that pos[] gathers them back into input order.
+// Between the two sit one device-side barrier each (all pairs have landed / all answers have landed); no collective
+// moves data and no send or receive staging buffer exists.
+struct PeerPtrs { u64 *p[32]; };
+struct OwnerPeerArgs {
+    const u64 *hash; u32 n; u32 world; u32 rank; u64 base_index; u32 cap;
+    u32 *cursors;      // [world] + overflow flag, zeroed by the caller
+    u32 *pos;
+    PeerPtrs recv;     // recv.p[o] = owner o's receive buffer: world regions of cap (hash, index) pairs
+};
+__global__ void __launch_bounds__(256) k_owner_scatter_peers(OwnerPeerArgs a)
+{
+    __shared__ u32 cnt[32], basep[32];
+    const u32 per = (a.n + gridDim.x - 1) / gridDim.x;
+    const u32 lo = min(a.n, blockIdx.x * per), hi = min(a.n, lo + per);
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(cnt + owner_of_hash(a.hash[i], a.world), 1u);
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        basep[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(a.cursors + threadIdx.x, cnt[threadIdx.x]) : 0u;
+        if (basep[threadIdx.x] + cnt[threadIdx.x] > a.cap) a.cursors[a.world] = 1u;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const u64 h = a.hash[i];
+        const u32 o = owner_of_hash(h, a.world);
+        const u32 k = basep[o] + atomicAdd(cnt + o, 1u);
+        u32 p = 0xffffffffu;
+        if (k < a.cap) {
+            p = o * a.cap + k;
+            reinterpret_cast<ulonglong2 *>(a.recv.p[o])[(size_t)a.rank * a.cap + k] = make_ulonglong2(h, a.base_index + i);
+        }
+        a.pos[i] = p;
+    }
+}
+__global__ void __launch_bounds__(256) k_owner_pad_peers(OwnerPeerArgs a)
+{
+    const u32 o = blockIdx.y;
+    const u32 used = min(a.cursors[o], a.cap);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.recv.p[o]) + (size_t)a.rank * a.cap;
+    for (u32 k = used + blockIdx.x * blockDim.x + threadIdx.x; k < a.cap; k += gridDim.x * blockDim.x)
+        dst[k] = make_ulonglong2(0ULL, ~0ULL);
+}
+struct FirstPeerArgs {
+    const TableSlot *slots; const u64 *side_first; const u64 *slot_of;
+    u32 world; u32 rank; u32 cap;
+    PeerPtrs ret;      // ret.p[s] = rank s's return buffer: world regions of cap first indices (region = owner)
+};
+__global__ void __launch_bounds__(256) k_table_first_peers(FirstPeerArgs a)
+{
+    const u32 s = blockIdx.y;                                  // asking rank: region s of the local receive buffer
+    u64 *dst = a.ret.p[s] + (size_t)a.rank * a.cap;
+    const u64 *slot_of = a.slot_of + (size_t)s * a.cap;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < a.cap; k += gridDim.x * blockDim.x) {
+        const u64 sl = slot_of[k];
+        dst[k] = sl == ~0ULL ? *a.side_first : (sl == ~0ULL - 1 ? ~0ULL : a.slots[sl].first);
+    }
+}
+// first_index[i] = ret[pos[i]]: the answers, which arrive in send order, back in input order
+__global__ void __launch_bounds__(256) k_gather_first(const u64 *ret, const u32 *pos, u32 n, u64 *out)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 p = pos[i];
+        out[i] = p == 0xffffffffu ? ~0ULL : ret[p];
     }
 }
 

@@ -754,6 +754,77 @@ int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, ui
     CK_CUDA(ctx, cudaStreamSynchronize(st));
     return CK_OK;
 }
+int ck_dev_owner_partition_padded(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index,
+                                  uint32_t world, uint32_t bucket_capacity, uint64_t *send_pairs, uint32_t *pos, uint32_t *cursors_dev)
+{
+    if (!ctx || !hash64 || !send_pairs || !pos || !cursors_dev || world < 1 || world > 32 || !bucket_capacity ||
+        (u64)world * bucket_capacity > 0xffffffffull)
+        return ctx ? fail(ctx, CK_ERR_ARG, "bad partition arguments") : CK_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK_CUDA(ctx, cudaMemsetAsync(cursors_dev, 0, (world + 1) * sizeof(u32), st));
+    OwnerPadArgs a{U(hash64), n, world, base_index, bucket_capacity, cursors_dev, U(send_pairs), pos};
+    if (n) {
+        k_owner_scatter_padded<<<std::min<u32>((n + 255) / 256, 8u * (u32)ctx->num_sms), 256, 0, st>>>(a);
+        ctx->launches++;
+    }
+    k_owner_pad<<<dim3(16, world), 256, 0, st>>>(a);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_owner_scatter_peers(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index,
+                               uint32_t world, uint32_t rank, uint32_t bucket_capacity, const uint64_t *peer_recv_ptrs,
+                               uint32_t *pos, uint32_t *cursors_dev)
+{
+    if (!ctx || !hash64 || !peer_recv_ptrs || !pos || !cursors_dev || world < 1 || world > 32 || rank >= world || !bucket_capacity ||
+        (u64)world * bucket_capacity > 0xffffffffull)
+        return ctx ? fail(ctx, CK_ERR_ARG, "bad partition arguments") : CK_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK_CUDA(ctx, cudaMemsetAsync(cursors_dev, 0, (world + 1) * sizeof(u32), st));
+    OwnerPeerArgs a{};
+    a.hash = U(hash64); a.n = n; a.world = world; a.rank = rank; a.base_index = base_index; a.cap = bucket_capacity;
+    a.cursors = cursors_dev; a.pos = pos;
+    for (u32 o = 0; o < world; o++) {
+        if (!peer_recv_ptrs[o]) return fail(ctx, CK_ERR_ARG, "null peer pointer");
+        a.recv.p[o] = reinterpret_cast<u64 *>(peer_recv_ptrs[o]);
+    }
+    if (n) {
+        k_owner_scatter_peers<<<std::min<u32>((n + 255) / 256, 8u * (u32)ctx->num_sms), 256, 0, st>>>(a);
+        ctx->launches++;
+    }
+    k_owner_pad_peers<<<dim3(16, world), 256, 0, st>>>(a);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_table_first_peers(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *slot_scratch,
+                             uint32_t world, uint32_t rank, uint32_t bucket_capacity, const uint64_t *peer_ret_ptrs)
+{
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !slot_scratch || !peer_ret_ptrs || world < 1 || world > 32 || rank >= world || !bucket_capacity ||
+        !table_view(table, table_bytes, slots, nslots, side, ov))
+        return ctx ? fail(ctx, CK_ERR_ARG, "bad table or peer arguments") : CK_ERR_ARG;
+    FirstPeerArgs a{};
+    a.slots = slots; a.side_first = side; a.slot_of = U(slot_scratch); a.world = world; a.rank = rank; a.cap = bucket_capacity;
+    for (u32 s = 0; s < world; s++) {
+        if (!peer_ret_ptrs[s]) return fail(ctx, CK_ERR_ARG, "null peer pointer");
+        a.ret.p[s] = reinterpret_cast<u64 *>(peer_ret_ptrs[s]);
+    }
+    const u32 gx = std::max<u32>(1u, std::min<u32>((bucket_capacity + 255) / 256, (8u * (u32)ctx->num_sms + world - 1) / world));
+    k_table_first_peers<<<dim3(gx, world), 256, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const uint32_t *pos, uint32_t n, uint64_t *out_first_index)
+{
+    if (!ctx || !ret || !pos || !out_first_index) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
+    if (!n) return CK_OK;
+    k_gather_first<<<std::min<u32>((n + 255) / 256, 16u * (u32)ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(U(ret), pos, n, U(out_first_index));
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
 uint64_t ck_launch_count(const ck_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int ck_kernel_timing(ck_ctx *ctx, int enable)

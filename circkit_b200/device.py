@@ -149,6 +149,7 @@ class OwnerPartitioner:
         self.pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.counts_dev = torch.zeros(2 * world, dtype=torch.int32, device=dev)
         self.counts_host = (C.c_uint32 * world)()
+        self._padded, self._state = None, None
 
     def __call__(self, hash64: torch.Tensor, base_index: int, world: int):
         n = hash64.numel()
@@ -157,6 +158,72 @@ class OwnerPartitioner:
                                                              _p(self.pairs), _p(self.pos), _p(self.counts_dev),
                                                              self.counts_host))
         return self.pairs[:n], self.pos[:n], [int(c) for c in self.counts_host]
+
+    def bucket_capacity(self, n: int) -> int:
+        """entries per fixed-capacity bucket: the mean n / world plus 8 standard deviations of a uniform split"""
+        return exchange_bucket_capacity(n, self.world)
+
+    def padded(self, hash64: torch.Tensor, base_index: int, world: int):
+        """fixed-capacity buckets for the equal-split exchange (no counts, no host synchronisation):
+        -> (pairs int64[world * cap, 2], pos int32[n], state int32[world + 1]: per-owner counts, then the overflow flag)"""
+        n = hash64.numel()
+        cap = self.bucket_capacity(n)
+        assert world == self.world and n <= self.pos.shape[0]
+        if self._padded is None or self._padded.shape[0] != world * cap:
+            self._padded = torch.empty((world * cap, 2), dtype=torch.int64, device=self.pos.device)
+            self._state = torch.zeros(world + 1, dtype=torch.int32, device=self.pos.device)
+        self.ctx._check(self.ctx._lib.ck_dev_owner_partition_padded(self.ctx.handle, _stream(), _p(hash64), n, base_index, world,
+                                                                    cap, _p(self._padded), _p(self.pos), _p(self._state)))
+        return self._padded, self.pos[:n], self._state
+
+
+class PeerExchange:
+    """Multi-GPU uniq's hash-range exchange fused into the kernels around it: the partition kernel stores every
+    (hash, index) pair straight into its owner's receive buffer over NVLink, the owner's query kernel stores every answer
+    straight into the asking rank's return buffer; two device-side barriers, no collective on the data path, no host
+    synchronisation.  torch symmetric memory maps the buffers of all ranks into every process and provides the barrier.
+
+    first_index(hash64, base_index, table, out) -> state int32[world + 1]; state[world] != 0: a bucket overflowed, `out`
+    is not valid and the batch must be repeated through exchange.exchange_first_index (checked by the caller, once,
+    after everything has been queued).  Every rank must call it for every batch (the barriers are collective)."""
+
+    def __init__(self, ctx: Context, n_max: int, world: int, rank: int, dev=None, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = dev or torch.device("cuda", ctx.device)
+        self.ctx, self.world, self.rank = ctx, world, rank
+        self.cap = exchange_bucket_capacity(n_max, world)
+        m = world * self.cap
+        self.m = m
+        self.recv = symm_mem.empty((m, 2), dtype=torch.int64, device=dev)
+        self.ret = symm_mem.empty(m, dtype=torch.int64, device=dev)
+        group = group or dist.group.WORLD
+        self.h_recv = symm_mem.rendezvous(self.recv, group)
+        self.h_ret = symm_mem.rendezvous(self.ret, group)
+        self.recv_ptrs = (C.c_uint64 * world)(*[int(p) for p in self.h_recv.buffer_ptrs])
+        self.ret_ptrs = (C.c_uint64 * world)(*[int(p) for p in self.h_ret.buffer_ptrs])
+        self.pos = torch.empty(max(n_max, 1), dtype=torch.int32, device=dev)
+        self.state = torch.zeros(world + 1, dtype=torch.int32, device=dev)
+        self.slots = torch.empty(m, dtype=torch.int64, device=dev)
+
+    def first_index(self, hash64: torch.Tensor, base_index: int, table: "DeviceTable", out: torch.Tensor) -> torch.Tensor:
+        n = hash64.numel()
+        assert n <= self.pos.shape[0] and out.numel() >= n
+        lib, h = self.ctx._lib, self.ctx.handle
+        self.ctx._check(lib.ck_dev_owner_scatter_peers(h, _stream(), _p(hash64), n, base_index, self.world, self.rank, self.cap,
+                                                       self.recv_ptrs, _p(self.pos), _p(self.state)))
+        self.h_recv.barrier()                       # every rank's pairs (and padding) have landed here
+        table.insert_pairs(self.recv, self.m, self.slots)
+        self.ctx._check(lib.ck_dev_table_first_peers(h, _stream(), _p(table.buf), table.bytes, _p(self.slots), self.world,
+                                                     self.rank, self.cap, self.ret_ptrs))
+        self.h_ret.barrier()                        # every owner's answers have landed here
+        self.ctx._check(lib.ck_dev_gather_first(h, _stream(), _p(self.ret), _p(self.pos), n, _p(out)))
+        return self.state
+
+
+def exchange_bucket_capacity(n: int, world: int) -> int:
+    mean = n / world
+    return int(mean + 8.0 * (mean ** 0.5) + 64) + 1
 
 
 def kernel_times(ctx: Context):

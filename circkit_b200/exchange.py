@@ -109,6 +109,61 @@ def exchange_first_index(hash64: torch.Tensor, base_index: int,
     return f_back[pos]                                     # back to input order
 
 
+def bucket_capacity(n: int, world: int) -> int:
+    """entries per fixed-capacity bucket: the mean n / world plus 8 standard deviations of a uniform split
+    (the same figure as device.exchange_bucket_capacity)"""
+    mean = n / world
+    return int(mean + 8.0 * (mean ** 0.5) + 64) + 1
+
+
+def _padded_partition_torch(hash64: torch.Tensor, base_index: int, world: int):
+    """device.OwnerPartitioner.padded with torch ops (CPU tests): fixed-capacity buckets, index -1 = no record"""
+    n = hash64.numel()
+    cap = bucket_capacity(n, world)
+    owner = owner_of(hash64, world)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world)
+    starts = torch.cumsum(counts, 0) - counts
+    rank_in_bucket = torch.arange(n, dtype=torch.int64, device=hash64.device) - starts[owner[order]]
+    pairs = torch.zeros((world * cap, 2), dtype=torch.int64, device=hash64.device)
+    pairs[:, 1] = -1
+    ok = rank_in_bucket < cap
+    dst = owner[order] * cap + rank_in_bucket
+    gidx = torch.arange(base_index, base_index + n, dtype=torch.int64, device=hash64.device)
+    pairs[dst[ok], 0] = hash64[order][ok]
+    pairs[dst[ok], 1] = gidx[order][ok]
+    pos = torch.full((n,), -1, dtype=torch.int64, device=hash64.device)
+    pos[order[ok]] = dst[ok]
+    state = torch.cat([counts.to(torch.int32), (~ok).any().to(torch.int32).reshape(1)])
+    return pairs, pos, state
+
+
+def _all_to_all_equal(send: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        return recv
+    each = send.shape[0] // world
+    return _all_to_all(send, [each] * world, [each] * world, group)
+
+
+def exchange_first_index_padded(hash64: torch.Tensor, base_index: int, first_pairs_fn, group=None, padded_fn=None):
+    """exchange_first_index without counts and without host synchronisation: every rank sends `world` buckets of one
+    fixed capacity (bucket_capacity: mean + 8 sigma of a uniform split, < 1 % padding at a million records per
+    bucket) with an equal-split all-to-all; unused entries carry index -1, which first_pairs_fn must answer with -1.
+
+    -> (first_index int64[n], state int32[world + 1]).  state[world] != 0 means that a bucket overflowed (a heavily
+    duplicated key set) and first_index is NOT valid: the caller repeats the batch through exchange_first_index.
+    The check is left to the caller so that it can be made once per batch, after everything has been queued."""
+    world = dist.get_world_size(group)
+    pairs, pos, state = (padded_fn or _padded_partition_torch)(hash64, base_index, world)
+    p_recv = _all_to_all_equal(pairs, group)
+    f_recv = first_pairs_fn(p_recv)
+    f_back = _all_to_all_equal(f_recv.contiguous(), group)
+    return f_back[pos.long()], state
+
+
 # ---- the same exchange in two phases, so that a rank can overlap it with the canonicalisation of its next sub-batch ----
 class PendingExchange:
     """State between exchange_send and exchange_finish: where every local record went and what this rank received."""

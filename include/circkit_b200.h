@@ -139,6 +139,32 @@ int ck_dev_owner_partition(ck_ctx *ctx, void *stream, const uint64_t *hash64, ui
                            uint64_t *send_pairs, uint32_t *pos, uint32_t *counts_dev, uint32_t *counts_host);
 int ck_dev_table_insert_pairs(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *pairs, uint32_t n,
                               uint64_t *slot_scratch);
+/* The same partition into FIXED-capacity buckets, for an equal-split all-to-all with no counts to exchange and no host
+ * synchronisation: bucket o = send_pairs[o * bucket_capacity, (o + 1) * bucket_capacity) (2 u64 per entry); unused entries
+ * carry index ~0, which ck_dev_table_insert_pairs skips (their first index reads back as ~0); pos[i] = entry of record i
+ * (0xffffffff if its bucket was full).  cursors_dev: world + 1 u32 of device scratch; after the call cursors_dev[o] =
+ * records sent to owner o and cursors_dev[world] != 0 iff a bucket overflowed -- the caller then repeats the batch with
+ * ck_dev_owner_partition.  Nothing is copied to the host and the stream is not synchronised. */
+int ck_dev_owner_partition_padded(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index,
+                                  uint32_t world, uint32_t bucket_capacity, uint64_t *send_pairs, uint32_t *pos,
+                                  uint32_t *cursors_dev);
+/* The exchange fused into the kernels around it, over peer-mapped device memory (one process per GPU of one NVLink /
+ * NVSwitch node; the caller maps every rank's buffers into every process, e.g. CUDA IPC or torch symmetric memory):
+ *   peer_recv_ptrs[o]  device address, in THIS process, of owner o's receive buffer: world regions of bucket_capacity
+ *                      (hash64, index) pairs; this rank writes region `rank` of every one of them, padding included;
+ *   peer_ret_ptrs[s]   device address of rank s's return buffer: world regions of bucket_capacity first indices;
+ *                      the owner writes region `rank` (= itself) with the answers for the pairs rank s sent, in order.
+ * Sequence per batch on every rank: ck_dev_owner_scatter_peers; barrier over all ranks; ck_dev_table_insert_pairs over the
+ * local receive buffer (world * bucket_capacity entries); ck_dev_table_first_peers; barrier; first_index[i] =
+ * own return buffer[pos[i]].  cursors_dev as in ck_dev_owner_partition_padded (overflow flag at [world]).  Neither call
+ * synchronises the stream.  Both pointer arrays are host arrays of `world` entries. */
+int ck_dev_owner_scatter_peers(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index,
+                               uint32_t world, uint32_t rank, uint32_t bucket_capacity, const uint64_t *peer_recv_ptrs,
+                               uint32_t *pos, uint32_t *cursors_dev);
+int ck_dev_table_first_peers(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes, const uint64_t *slot_scratch,
+                             uint32_t world, uint32_t rank, uint32_t bucket_capacity, const uint64_t *peer_ret_ptrs);
+/* out_first_index[i] = ret[pos[i]] (~0 where pos[i] == 0xffffffff): answers of either fixed-capacity exchange back in input order */
+int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const uint32_t *pos, uint32_t n, uint64_t *out_first_index);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ck_launch_count(const ck_ctx *ctx);
 /* per-class kernel timing for the roofline: when enabled, every length/alphabet-class launch is bracketed

@@ -143,3 +143,60 @@ def test_owner_of_covers_unsigned_range():
     r = np.sort(np.random.default_rng(0).integers(0, 2**64, size=1000, dtype=np.uint64))
     o = owner_of(torch.from_numpy(r.view(np.int64).copy()), 8).numpy()
     assert (np.diff(o) >= 0).all() and o.min() == 0 and o.max() == 7
+
+
+def _first_pairs_skipping_padding(pairs: torch.Tensor) -> torch.Tensor:
+    """stand-in for ck_dev_table_insert_pairs + ck_dev_table_first: padding entries (index -1) answer -1"""
+    out = torch.full((pairs.shape[0],), -1, dtype=torch.int64)
+    real = pairs[:, 1] >= 0
+    out[real] = _min_index_per_key(pairs[real, 0].contiguous(), pairs[real, 1].contiguous())
+    return out
+
+
+def _worker_padded(rank, world, port, hashes, expected, overflow_expected, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from circkit_b200 import exchange as X
+    n = len(hashes) // world
+    lo, hi = rank * n, (rank + 1) * n if rank < world - 1 else len(hashes)
+    h = torch.from_numpy(hashes[lo:hi].view(np.int64).copy())
+    first, state = X.exchange_first_index_padded(h, lo, _first_pairs_skipping_padding)
+    # one flag for the whole job: every rank repeats through the exact path if any bucket anywhere overflowed
+    flag = state[world: world + 1].clone().to(torch.int64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    overflowed = bool(flag.item())
+    if overflowed:
+        first = X.exchange_first_index(h, lo, _min_index_per_key)
+    ok = np.array_equal(first.numpy().astype(np.uint64), expected[lo:hi]) and overflowed == overflow_expected
+    ok = ok and int(state[:world].sum()) == hi - lo
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,skewed", [(2, False), (3, False), (2, True)])
+def test_padded_exchange_matches_serial_consumer(world, skewed):
+    """fixed-capacity buckets + equal-split all-to-all; a skewed key set (most records share one key) overflows a
+    bucket, is reported, and the exact path gives the answer"""
+    import oracle
+    from oracle import synth
+    arena, off = synth.make_records(3000, 0, 60, 120, 400, seed=20 + world)
+    res = oracle.canonicalize_batch(arena, off, normalize=True, threads=2, want_start=False)
+    hashes, expected = oracle.uniq_consume(res["out"], off, res["lens"])
+    if skewed:
+        hashes = hashes.copy()
+        hashes[::2] = hashes[0]                                   # half of the records are copies of record 0
+        first_of = {}
+        expected = np.array([first_of.setdefault(int(k), i) for i, k in enumerate(hashes)], dtype=np.uint64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_padded, args=(r, world, port, hashes.copy(), expected, skewed, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(r, True) for r in range(world)]

@@ -241,3 +241,43 @@ def test_prepare_any_alignment_and_every_path(env, normalize, skew):
     for i in range(n):
         a, ln = int(off[i]), int(got_len[i])                    # the oracle keeps record i at its raw offset
         assert out[starts[i]: starts[i] + ln].tobytes() == want["out"][a: a + ln].tobytes(), (i, seqs[i][:60])
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_padded_owner_partition(env, world):
+    """ck_dev_owner_partition_padded: fixed-capacity buckets for the equal-split exchange.  Every record sits in its
+    owner's bucket, the unused tail of every bucket carries index ~0, which the table skips (first index ~0), and an
+    overflowing bucket (one key repeated) raises the flag instead of writing past the bucket."""
+    ctx, D, torch = env
+    from circkit_b200.exchange import owner_of, bucket_capacity
+    n, base = 300_006, 5_000_000_000
+    g = torch.Generator(device="cuda").manual_seed(10 + world)
+    h = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    h[n // 2:] = h[: n - n // 2].clone()                                      # repeated keys: first index < own index
+    part = D.OwnerPartitioner(ctx, n, world)
+    cap = part.bucket_capacity(n)
+    assert cap == bucket_capacity(n, world)
+    pairs, pos, state = part.padded(h, base, world)
+    own = owner_of(h, world)
+    assert state[:world].tolist() == torch.bincount(own, minlength=world).tolist() and int(state[world]) == 0
+    assert pairs.shape == (world * cap, 2)
+    p = pos.long()
+    assert torch.equal(pairs[p, 0], h) and torch.equal(pairs[p, 1], torch.arange(base, base + n, device="cuda"))
+    assert torch.equal(p // cap, own)
+    used = torch.zeros(world * cap, dtype=torch.bool, device="cuda"); used[p] = True
+    assert int(used.sum()) == n and bool((pairs[~used, 1] == -1).all())
+    for o in range(world):                                                    # records first, padding behind them
+        assert bool(used[o * cap: o * cap + int(state[o])].all())
+    # owner side: padding is skipped and answers ~0; records get the minimum index of their key
+    table = D.DeviceTable(ctx, n)
+    m = world * cap
+    slots = torch.empty(m, dtype=torch.int64, device="cuda"); first = torch.empty_like(slots)
+    table.insert_pairs(pairs, m, slots); table.first(slots, m, first)
+    assert bool((first[~used] == -1).all())
+    want = torch.arange(base, base + n, device="cuda"); want[n // 2:] = want[: n - n // 2].clone()
+    assert torch.equal(first[p], want)
+    # overflow: every record carries the same key
+    h2 = torch.full((n,), 12345, dtype=torch.int64, device="cuda")
+    pairs2, pos2, state2 = part.padded(h2, base, world)
+    assert int(state2[world]) == 1 and int(state2[0]) == n
+    assert int((pos2.long() == 0xffffffff).sum() + (pos2 == -1).sum()) == n - cap
