@@ -149,7 +149,7 @@ int ck_dev_owner_partition_padded(ck_ctx *ctx, void *stream, const uint64_t *has
                                   uint32_t world, uint32_t bucket_capacity, uint64_t *send_pairs, uint32_t *pos,
                                   uint32_t *cursors_dev);
 /* The exchange fused into the kernels around it, over peer-mapped device memory (one process per GPU of one NVLink /
- * NVSwitch node; the caller maps every rank's buffers into every process, e.g. CUDA IPC or torch symmetric memory):
+ * NVSwitch node; the caller maps every rank's buffers into every process, e.g. with CUDA IPC handles):
  *   peer_recv_ptrs[o]  device address, in THIS process, of owner o's receive buffer: world regions of bucket_capacity
  *                      (hash64, index) pairs; this rank writes region `rank` of every one of them, padding included;
  *   peer_ret_ptrs[s]   device address of rank s's return buffer: world regions of bucket_capacity first indices;
