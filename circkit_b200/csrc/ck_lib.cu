@@ -16,6 +16,7 @@
 #include "ck_lane2.cuh"
 #include "ck_stream2.cuh"
 #include "ck_synth.cuh"
+#include "ck_monomerize.cuh"
 
 using namespace ck;
 
@@ -821,6 +822,25 @@ int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const ui
     if (!ctx || !ret || !pos || !out_first_index) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     if (!n) return CK_OK;
     k_gather_first<<<std::min<u32>((n + 255) / 256, 16u * (u32)ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(U(ret), pos, n, U(out_first_index));
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                      uint32_t seed_len, uint64_t overlap_dist, double overlap_min_identity, uint32_t flags, uint32_t *out_end_index)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (seed_len < 1 || seed_len > 63) return fail(ctx, CK_ERR_ARG, "Seed length must be at least 1 and at most 63");
+    if (overlap_min_identity >= 0.0 && overlap_dist)
+        return fail(ctx, CK_ERR_ARG, "Both overlap_dist and overlap_min_identity are set. They are mutually exclusive");
+    if (!n_records) return CK_OK;
+    if (!offsets || !out_end_index) return fail(ctx, CK_ERR_ARG, "null argument");
+    MonoArgs a{};
+    a.bytes = bytes; a.offsets = U(offsets); a.n_records = n_records; a.seed_len = seed_len;
+    a.use_identity = overlap_min_identity >= 0.0 ? 1u : 0u; a.overlap_dist = overlap_dist;
+    a.identity = overlap_min_identity; a.flags = flags; a.out_end = out_end_index;
+    const u32 grid = std::min<u32>((n_records + 7) / 8, 16u * (u32)ctx->num_sms);
+    k_monomerize<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;

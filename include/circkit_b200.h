@@ -165,6 +165,21 @@ int ck_dev_table_first_peers(ck_ctx *ctx, void *stream, void *table, uint64_t ta
                              uint32_t world, uint32_t rank, uint32_t bucket_capacity, const uint64_t *peer_ret_ptrs);
 /* out_first_index[i] = ret[pos[i]] (~0 where pos[i] == 0xffffffff): answers of either fixed-capacity exchange back in input order */
 int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const uint32_t *pos, uint32_t n, uint64_t *out_first_index);
+/* ---- monomerize (the step that feeds canonicalize / uniq in the author's pipeline, README.md:83) ----
+ * For every record of a device-resident batch of raw bytes (record i = bytes[offsets[i], offsets[i+1]), library semantics:
+ * bytes as they are) the end index of its last monomer:
+ *   Monomerizer::last_monomer_end_index            lib/src/monomerize.rs:100-125   (flags 0)
+ *   Monomerizer::last_monomer_end_index_sensitive  lib/src/monomerize.rs:127-141   (flags CK_MONO_SENSITIVE)
+ *   Monomerizer::first_monomer_end_index           lib/src/monomerize.rs:50-99     (flags CK_MONO_FIRST_ONLY)
+ * out_end_index[i] = CK_MONO_NONE for None; monomerize(seq) = seq[.. end] (the whole record for None, :144-158).
+ * overlap_min_identity < 0 means "not set" (then overlap_dist applies, default 0); the builder's rules hold
+ * (lib/src/monomerize.rs:20-40): 1 <= seed_len <= 63, identity and a non-zero distance exclude each other -> CK_ERR_ARG. */
+#define CK_MONO_SENSITIVE 1u
+#define CK_MONO_FIRST_ONLY 2u
+#define CK_MONO_NONE 0xffffffffu
+int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                      uint32_t seed_len, uint64_t overlap_dist, double overlap_min_identity, uint32_t flags,
+                      uint32_t *out_end_index);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ck_launch_count(const ck_ctx *ctx);
 /* per-class kernel timing for the roofline: when enabled, every length/alphabet-class launch is bracketed
