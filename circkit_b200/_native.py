@@ -58,7 +58,8 @@ SIGNATURES = {
     "ck_dev_owner_scatter_peers": (_i, [_vp, _vp, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ck_dev_table_first_peers": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp]),
     "ck_dev_gather_first": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
-    "ck_dev_monomerize": (_i, [_vp, _vp, _vp, _vp, _u32, _u32, _u64, C.c_double, _u32, _vp]),
+    "ck_dev_monomerize": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, C.c_double, _u32, _vp]),
+    "ck_dev_normalize": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "ck_launch_count": (_u64, [_vp]),
     "ck_kernel_timing": (_i, [_vp, _i]),
     "ck_kernel_times": (_i, [_vp, _vp, _vp, _u32]),

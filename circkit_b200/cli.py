@@ -327,6 +327,88 @@ def uniq(fasta: bytes, canonical: bool = False, table_ext: str | None = None):
     return out, (bytes(table) if table is not None else None)
 
 
+class CliError(ValueError):
+    """argument combinations the reference rejects with `bail!` (src/monomerize.rs:35-45)"""
+
+
+def monomerize(fasta: bytes, sensitive: bool = False, seed_length: int = 10, max_mismatch=None, min_identity=None,
+               min_overlap=None, min_overlap_percent=None, min_length: int = 0, max_length=None, keep_all: bool = False,
+               table_ext: str | None = None):
+    """bytes of a FASTA file -> (bytes `circkit monomerize` writes, bytes of the --table file or None)
+    (src/monomerize.rs:16-160).  Normalisation (`ck_dev_normalize`) and the monomer search (`ck_dev_monomerize`) run on
+    the device over the whole file as one batch; the length / overlap filters of the consumer closure (:102-135) and the
+    framing (:139-143: '>' head, full_seq[..end]) are vectorised on the host."""
+    import torch
+    from .monomerize import Monomerizer
+    if max_mismatch is not None and min_identity is not None:
+        raise CliError("cannot specify both max_mismatch and min_identity")
+    if min_identity is not None and not 0.0 <= min_identity <= 1.0:
+        raise CliError("min_identity must be between 0.0 and 1.0")
+    recs = Records(fasta)
+    n = len(recs)
+    table = bytearray() if table_ext is not None else None
+    if n == 0:
+        return b"", (bytes(table) if table is not None else None)
+    seq_len = (recs.seq_hi - recs.seq_lo).astype(np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(seq_len, out=off[1:])
+    arena = np.ascontiguousarray(recs.gather(recs.seq_lo, recs.seq_hi))
+    m = Monomerizer(seed_length, max_mismatch, min_identity)
+    ctx = m._context()
+    try:
+        dev = torch.device("cuda", ctx.device)
+        raw = torch.from_numpy(arena if len(arena) else np.zeros(1, dtype=np.uint8)).to(dev)
+        offs = torch.from_numpy(off).to(dev)
+        norm, nlens = m.normalize_device(raw, offs, n)
+        end = m.end_indices_device(norm, offs, n, sensitive=sensitive, lens=nlens)
+        idx = end.cpu().numpy().astype(np.int64)             # -1 = None
+        nl = nlens.cpu().numpy().astype(np.int64)
+    finally:
+        ctx.close()
+    idx[(nl < seed_length) | (nl < min_length)] = -1        # worker closure, src/monomerize.rs:92-96
+    # record.full_seq(): the lines of seq joined, each without its '\n' and one trailing '\r'
+    is_nl, is_cr = arena == 10, arena == 13
+    before_nl = np.append(is_nl[1:], False)
+    at_end = np.zeros(len(arena), dtype=bool)
+    nonempty = seq_len > 0
+    at_end[off[1:][nonempty] - 1] = True
+    kept = ~(is_nl | (is_cr & (before_nl | at_end)))
+    c = np.zeros(len(arena) + 1, dtype=np.int64)
+    np.cumsum(kept, out=c[1:])
+    full_len = c[off[1:]] - c[off[:-1]]
+    ok = idx >= 0                                            # consumer closure, :107-135
+    ok &= ~(idx < min_length)
+    if max_length is not None:
+        ok &= ~(idx > max_length)
+    if min_overlap is not None:
+        ok &= ~((full_len - idx) < min_overlap)
+    if min_overlap_percent is not None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ok &= ~(((full_len - idx).astype(np.float64) / idx.astype(np.float64)) < min_overlap_percent)
+    write = ok | keep_all
+    end_idx = np.minimum(np.where(ok, idx, full_len), full_len)
+    rec_of = np.repeat(np.arange(n, dtype=np.int64), seq_len)
+    rank = c[:-1] - c[off[:-1]][rec_of]
+    sel = kept & (rank < end_idx[rec_of]) & write[rec_of]
+    heads = recs.gather(recs.head_lo[write], recs.head_hi[write])
+    out = _assemble(heads, (recs.head_hi - recs.head_lo)[write], arena[sel], end_idx[write])
+    if table is not None:                                    # :145-154, csv 1.2.2 defaults: header with the first row
+        delim = b"\t" if table_ext == "tsv" else b","
+
+        def field(f: bytes) -> bytes:
+            if any(x in f for x in (delim, b'"', b"\n", b"\r")):
+                return b'"' + f.replace(b'"', b'""') + b'"'
+            return f
+        rows = np.flatnonzero(write)
+        if len(rows):
+            table += delim.join([b"id", b"original_length", b"monomer_length"]) + b"\n"
+        for i in rows.tolist():
+            head = recs.data[recs.head_lo[i]: recs.head_hi[i]].tobytes()
+            head.decode("utf-8")                             # std::str::from_utf8(record.head()).unwrap()
+            table += delim.join([field(head), b"%d" % full_len[i], b"%d" % end_idx[i]]) + b"\n"
+    return out, (bytes(table) if table is not None else None)
+
+
 # ------------------------------------------------------------------------------------------------ entry point
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="circkit", description="canonicalize / uniq on the B200 path")
@@ -343,11 +425,36 @@ def main(argv=None) -> int:
     u.add_argument("-c", "--canonicalize", "--norm", "--canon", dest="canonicalize", action="store_true")
     u.add_argument("--table")
     u.add_argument("-t", "--threads", type=int, default=os.cpu_count())
+    mo = sub.add_parser("monomerize")                          # src/commands.rs:19-90
+    mo.add_argument("input", nargs="?")
+    mo.add_argument("-o", "--output")
+    mo.add_argument("--sensitive", action="store_true")
+    mo.add_argument("--seed-length", type=int, default=10, choices=range(5, 65), metavar="[5..64]")
+    mo.add_argument("--max-mismatch", type=int)
+    mo.add_argument("--min-identity", type=float)
+    mo.add_argument("--min-overlap", type=int)
+    mo.add_argument("--min-overlap-percent", type=float)
+    mo.add_argument("--min-length", type=int, default=0)
+    mo.add_argument("--max-length", type=int)
+    mo.add_argument("-k", "--keep-all", action="store_true")
+    mo.add_argument("--table")
+    mo.add_argument("-t", "--threads", type=int, default=os.cpu_count())
+    mo.add_argument("--batch-size", type=int, default=64, help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
     try:
         data = read_input(args.input)
         if args.command in ("canonicalize", "canon"):
             write_output(args.output, canonicalize(data))
+        elif args.command == "monomerize":
+            ext = None
+            if args.table is not None:
+                ext = "tsv" if args.table.endswith(".tsv") else "csv"
+            out, table = monomerize(data, args.sensitive, args.seed_length, args.max_mismatch, args.min_identity, args.min_overlap,
+                                    args.min_overlap_percent, args.min_length, args.max_length, args.keep_all, ext)
+            write_output(args.output, out)
+            if args.table is not None:
+                with open(args.table, "wb") as f:
+                    f.write(table)
         else:
             ext = None
             if args.table is not None:
@@ -361,7 +468,7 @@ def main(argv=None) -> int:
         msg = e.strerror or str(e)
         print("Error: %s%s" % (msg, " (os error %d)" % e.errno if e.errno else ""), file=sys.stderr)
         return 1
-    except (FastaError, UnicodeDecodeError) as e:
+    except (FastaError, UnicodeDecodeError, CliError, ValueError) as e:
         print("Error: %s" % e, file=sys.stderr)
         return 1
     return 0

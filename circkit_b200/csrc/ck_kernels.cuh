@@ -204,6 +204,7 @@ __global__ void k_canon_empty(CanonArgs a)
 //   flags bit0 (normalise): needletail::sequence::normalize(seq, false) -- src/canonicalize.rs:24-27
 //                           (whitespace dropped, acgt -> upper, t/u/U -> T, ./~ -> -, anything else -> N)
 //   otherwise             : library semantics, bytes are taken as they are (lib/src/canonicalize.rs:54)
+//   flags bit1            : write the (normalised) bytes of EVERY record, whatever its alphabet class (ck_dev_normalize)
 // Writes lens[i], lane[i] (2, 4 or 8 bits per symbol) and the record in that lane's format:
 //   lane 2 -> packed2 at word p2_word(offsets[i], i);   lanes 4/8 -> normalised bytes at offsets[i].
 // Pass 1 classifies and counts through a 256-entry shared-memory table (mapped byte | keep | not-ACGT | not-16-symbol);
@@ -337,14 +338,15 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
         cnt = __reduce_add_sync(CK_FULL, cnt);
         fl = __reduce_or_sync(CK_FULL, fl);
         const u32 lanebits = (fl & 0x400u) ? 8u : (fl & 0x200u) ? 4u : 2u;
-        if (lane == 0) { a.lens[rec] = cnt; a.lane[rec] = (u8)lanebits; }
+        if (lane == 0) { a.lens[rec] = cnt; if (a.lane) a.lane[rec] = (u8)lanebits; }
+        const bool pack2 = lanebits == 2 && !(a.flags & 2u);       // flags bit1: normalised bytes for every record (ck_dev_normalize)
         if (rawlen == 0) continue;
         // pass 2: write in the lane's format
         const u32 sh = (u32)((size_t)src & 15u);
         const uint4 *src16 = reinterpret_cast<const uint4 *>(src - sh);
         const u32 span = sh + rawlen;                   // bytes from *src16 to the end of the record
         u32 *dst32 = reinterpret_cast<u32 *>(a.packed2 + p2_word(off, rec));     // 16-base units in address order
-        if (cnt == rawlen && lanebits == 2) {            // nothing dropped: pack straight from the raw bytes
+        if (cnt == rawlen && pack2) {                    // nothing dropped: pack straight from the raw bytes
             for (u32 base = 0; base < rawlen; base += 512) {
                 const u32 p = base + 16 * lane;
                 if (p < rawlen) {
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
             continue;
         }
         // general path: compact the kept bytes through the stage, laid out congruent to the destination
-        u32 S = lanebits == 2 ? 0u : A;                  // stage[S ..) <-> next symbol to place
+        u32 S = pack2 ? 0u : A;                          // stage[S ..) <-> next symbol to place
         u32 done = 0;                                    // 2-bit: full units stored; bytes: bytes stored
         for (u32 base = 0; base < rawlen; base += 512) {
             const u32 p = base + 16 * lane;
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
                 if ((mask >> k) & 1u) stage[idx++] = (u8)prep_byte(m, k);
             __syncwarp();
             const u32 fill = S + T;                                  // stage[0, fill) is valid
-            if (lanebits == 2) {
+            if (pack2) {
                 const u32 U = fill >> 4;
                 for (u32 j = lane; j < U; j += 32) dst32[done + j] = prep_pack16(*reinterpret_cast<const uint4 *>(stage + 16 * j));
                 const u32 r = fill & 15u;
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
             }
         }
         __syncwarp();
-        if (lanebits == 2 && S && lane == 0)
+        if (pack2 && S && lane == 0)
             dst32[done] = prep_pack16(*reinterpret_cast<const uint4 *>(stage)) & ~(0xffffffffu >> (2 * S));
         __syncwarp();
     }

@@ -826,7 +826,19 @@ int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const ui
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }
-int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+int ck_dev_normalize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                     uint8_t *out_bytes, uint32_t *out_len)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (!n_records) return CK_OK;
+    if (!offsets || !out_bytes || !out_len) return fail(ctx, CK_ERR_ARG, "null argument");
+    PrepareArgs pa{bytes, U(offsets), n_records, 1u | 2u, nullptr, out_bytes, out_len, nullptr};
+    k_prepare<<<ctx->num_sms * 32, 256, 0, (cudaStream_t)stream>>>(pa);
+    ctx->launches++;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, const uint32_t *lens, uint32_t n_records,
                       uint32_t seed_len, uint64_t overlap_dist, double overlap_min_identity, uint32_t flags, uint32_t *out_end_index)
 {
     if (!ctx) return CK_ERR_ARG;
@@ -836,7 +848,7 @@ int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uin
     if (!n_records) return CK_OK;
     if (!offsets || !out_end_index) return fail(ctx, CK_ERR_ARG, "null argument");
     MonoArgs a{};
-    a.bytes = bytes; a.offsets = U(offsets); a.n_records = n_records; a.seed_len = seed_len;
+    a.bytes = bytes; a.offsets = U(offsets); a.lens = lens; a.n_records = n_records; a.seed_len = seed_len;
     a.use_identity = overlap_min_identity >= 0.0 ? 1u : 0u; a.overlap_dist = overlap_dist;
     a.identity = overlap_min_identity; a.flags = flags; a.out_end = out_end_index;
     const u32 grid = std::min<u32>((n_records + 7) / 8, 16u * (u32)ctx->num_sms);

@@ -21,7 +21,7 @@ namespace ck {
 #endif
 
 struct MonoArgs {
-    const u8 *bytes; const u64 *offsets; u32 n_records;
+    const u8 *bytes; const u64 *offsets; const u32 *lens; u32 n_records;   // lens: optional normalised lengths (ck_dev_normalize)
     u32 seed_len;          // 1 .. 63
     u32 use_identity;      // 1: max distance = len - floor(len * identity) (f64, as the reference computes it)
     u64 overlap_dist;      // 0: otherwise
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_monomerize(MonoArgs a)
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 rec = gw; rec < a.n_records; rec += nw) {
         const u64 off = a.offsets[rec];
-        const u32 n = (u32)(a.offsets[rec + 1] - off);
+        const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
         const u8 *seq = a.bytes + off;
         u32 idx = mono_first<false>(a, MonoView<false>{seq, n});
         if (!(a.flags & 2u)) {

@@ -57,15 +57,25 @@ class Monomerizer:
         return [None if v == N.CK_MONO_NONE else int(v) for v in out.cpu().numpy().astype(np.uint32).tolist()]
 
     def end_indices_device(self, raw: torch.Tensor, offsets: torch.Tensor, n: int, sensitive: bool = False,
-                           first_only: bool = False) -> torch.Tensor:
-        """resident batch (uint8 bytes, int64 offsets[n + 1]) -> int32[n] end indices (bit pattern 0xffffffff = None)"""
+                           first_only: bool = False, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """resident batch (uint8 bytes, int64 offsets[n + 1], optional int32 lens[n]: record i is its first lens[i] bytes)
+        -> int32[n] end indices (bit pattern 0xffffffff = None)"""
         ctx = self._context()
         out = torch.empty(max(n, 1), dtype=torch.int32, device=raw.device)
         flags = (N.CK_MONO_SENSITIVE if sensitive else 0) | (N.CK_MONO_FIRST_ONLY if first_only else 0)
         ident = -1.0 if self.overlap_min_identity is None else float(self.overlap_min_identity)
-        ctx._check(ctx._lib.ck_dev_monomerize(ctx.handle, _stream(), _p(raw), _p(offsets), n, self.seed_len,
+        ctx._check(ctx._lib.ck_dev_monomerize(ctx.handle, _stream(), _p(raw), _p(offsets), _p(lens), n, self.seed_len,
                                               int(self.overlap_dist or 0), ident, flags, _p(out)))
         return out[:n]
+
+    def normalize_device(self, raw: torch.Tensor, offsets: torch.Tensor, n: int):
+        """needletail normalisation of a resident batch (the CLI's first step, src/monomerize.rs:86-89):
+        -> (bytes uint8 like raw, lens int32[n])"""
+        ctx = self._context()
+        out = torch.empty(raw.numel() + 64, dtype=torch.uint8, device=raw.device)
+        lens = torch.empty(max(n, 1), dtype=torch.int32, device=raw.device)
+        ctx._check(ctx._lib.ck_dev_normalize(ctx.handle, _stream(), _p(raw), _p(offsets), n, _p(out), _p(lens)))
+        return out, lens[:n]
 
     # ---- the reference's per-sequence methods
     def first_monomer_end_index(self, seq: bytes) -> Optional[int]:

@@ -166,8 +166,8 @@ int ck_dev_table_first_peers(ck_ctx *ctx, void *stream, void *table, uint64_t ta
 /* out_first_index[i] = ret[pos[i]] (~0 where pos[i] == 0xffffffff): answers of either fixed-capacity exchange back in input order */
 int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const uint32_t *pos, uint32_t n, uint64_t *out_first_index);
 /* ---- monomerize (the step that feeds canonicalize / uniq in the author's pipeline, README.md:83) ----
- * For every record of a device-resident batch of raw bytes (record i = bytes[offsets[i], offsets[i+1]), library semantics:
- * bytes as they are) the end index of its last monomer:
+ * For every record of a device-resident batch of raw bytes (record i = bytes[offsets[i], offsets[i+1]) or, with `lens`,
+ * its first lens[i] bytes; library semantics: bytes as they are) the end index of its last monomer:
  *   Monomerizer::last_monomer_end_index            lib/src/monomerize.rs:100-125   (flags 0)
  *   Monomerizer::last_monomer_end_index_sensitive  lib/src/monomerize.rs:127-141   (flags CK_MONO_SENSITIVE)
  *   Monomerizer::first_monomer_end_index           lib/src/monomerize.rs:50-99     (flags CK_MONO_FIRST_ONLY)
@@ -177,9 +177,14 @@ int ck_dev_gather_first(ck_ctx *ctx, void *stream, const uint64_t *ret, const ui
 #define CK_MONO_SENSITIVE 1u
 #define CK_MONO_FIRST_ONLY 2u
 #define CK_MONO_NONE 0xffffffffu
-int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
-                      uint32_t seed_len, uint64_t overlap_dist, double overlap_min_identity, uint32_t flags,
+int ck_dev_monomerize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, const uint32_t *lens,
+                      uint32_t n_records, uint32_t seed_len, uint64_t overlap_dist, double overlap_min_identity, uint32_t flags,
                       uint32_t *out_end_index);
+/* needletail::sequence::normalize(seq, false) of every record of a resident batch (src/monomerize.rs:86-89,
+ * src/canonicalize.rs:24): out_bytes holds record i's normalised bytes at offsets[i], out_len[i] of them (white space is
+ * dropped, so out_len[i] <= offsets[i+1] - offsets[i]); feed both to ck_dev_monomerize (`lens`) for the CLI's semantics. */
+int ck_dev_normalize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                     uint8_t *out_bytes, uint32_t *out_len);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ck_launch_count(const ck_ctx *ctx);
 /* per-class kernel timing for the roofline: when enabled, every length/alphabet-class launch is bracketed

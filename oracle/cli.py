@@ -132,3 +132,48 @@ def cli_uniq(fasta: bytes, canonicalize: bool = False, table_ext: str | None = N
                 wrote_header = True
             table += _csv_field(recs[int(first[i])].id, delim) + delim + _csv_field(r.id, delim) + b"\n"
     return bytes(out), (bytes(table) if table is not None else None)
+
+
+def full_seq(seq: bytes) -> bytes:
+    """seq_io 0.3.2 fasta Record::full_seq: the sequence lines joined, each without its '\\n' and one trailing '\\r'"""
+    return b"".join(_trim_cr(line) for line in seq.split(b"\n"))
+
+
+def cli_monomerize(fasta: bytes, sensitive: bool = False, seed_length: int = 10, max_mismatch=None, min_identity=None,
+                   min_overlap=None, min_overlap_percent=None, min_length: int = 0, max_length=None, keep_all: bool = False,
+                   table_ext: str | None = None):
+    """src/monomerize.rs:16-160 -> (bytes of -o, bytes of --table or None).  Worker (:83-101): normalise (None -> the raw
+    seq), too short for the seed or for --min-length -> None, else last_monomer_end_index[_sensitive] of the NORMALISED
+    sequence.  Consumer (:102-150): filters on the monomer length / overlap, then '>' head '\\n' full_seq[..end] '\\n' and
+    the table row (id = the whole head, original_length, monomer_length)."""
+    from . import normalize
+    from .monomerize import Monomerizer
+    if max_mismatch is not None and min_identity is not None:
+        raise ValueError("cannot specify both max_mismatch and min_identity")
+    if min_identity is not None and not 0.0 <= min_identity <= 1.0:
+        raise ValueError("min_identity must be between 0.0 and 1.0")
+    m = Monomerizer(seed_length, max_mismatch, min_identity)
+    out, table = bytearray(), (bytearray() if table_ext is not None else None)
+    delim = b"\t" if table_ext == "tsv" else b","
+    for r in parse_fasta(fasta):
+        norm = normalize(r.seq)
+        idx = None
+        if not (len(norm) < seed_length or len(norm) < min_length):
+            idx = m.last_monomer_end_index_sensitive(norm) if sensitive else m.last_monomer_end_index(norm)
+        fs = full_seq(r.seq)
+        if idx is not None and (idx < min_length or (max_length is not None and idx > max_length)):
+            idx = None
+        if min_overlap is not None and idx is not None and len(fs) - idx < min_overlap:
+            idx = None
+        if min_overlap_percent is not None and idx is not None:
+            ratio = (len(fs) - idx) / idx if idx else (float("inf") if len(fs) else float("nan"))
+            if ratio < min_overlap_percent:
+                idx = None
+        if idx is not None or keep_all:
+            end = len(fs) if idx is None else idx
+            out += b">" + r.head + b"\n" + fs[:end] + b"\n"
+            if table is not None:
+                if not table:
+                    table += delim.join([b"id", b"original_length", b"monomer_length"]) + b"\n"
+                table += delim.join([_csv_field(r.head, delim), b"%d" % len(fs), b"%d" % end]) + b"\n"
+    return bytes(out), (bytes(table) if table is not None else None)

@@ -60,7 +60,7 @@ def test_builder_validation_matches_reference(ctx):
     import torch
     z = torch.zeros(2, dtype=torch.int64, device="cuda"); o = torch.zeros(1, dtype=torch.int32, device="cuda")
     for seed, dist, ident in ((0, 0, -1.0), (64, 0, -1.0), (4, 1, 0.95)):
-        rc = ctx._lib.ck_dev_monomerize(ctx.handle, None, None, z.data_ptr(), 1, seed, dist, ident, 0, o.data_ptr())
+        rc = ctx._lib.ck_dev_monomerize(ctx.handle, None, None, z.data_ptr(), None, 1, seed, dist, ident, 0, o.data_ptr())
         assert rc == -2                                       # CK_ERR_ARG
 
 
