@@ -37,8 +37,8 @@ def test_peer_exchange_one_rank_matches_table(env):
     n, base = 400_000, 9_000_000_000
     g = torch.Generator(device="cuda").manual_seed(3)
     h = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
-    h[n // 2:] = h[: n // 2].clone()                                          # every key twice
     h[7] = -1                                                                 # the key that equals the table's empty marker
+    h[n // 2:] = h[: n // 2].clone()                                          # every key twice
     peer = D.PeerExchange(ctx, n, 1, 0)
     table = D.DeviceTable(ctx, n)
     out = torch.empty(n, dtype=torch.int64, device="cuda")
