@@ -711,31 +711,64 @@ struct OwnerPeerArgs {
     u32 *pos;
     PeerPtrs recv;     // recv.p[o] = owner o's receive buffer: world regions of cap (hash, index) pairs
 };
+// Tiles of 2048 records are bucketed in shared memory first, so that what crosses NVLink are runs of consecutive 16-byte
+// pairs per owner (a tile holds ~256 pairs per owner at 8 ranks) written by consecutive threads, not single pairs
+// scattered over eight destinations (8 GPUs, 12.5 M records: 0.55 ms with per-record remote stores).
+#define CK_SCAT_TILE 2048u
 __global__ void __launch_bounds__(256) k_owner_scatter_peers(OwnerPeerArgs a)
 {
-    __shared__ u32 cnt[32], basep[32];
+    __shared__ ulonglong2 stage[CK_SCAT_TILE];
+    __shared__ u8 own[CK_SCAT_TILE];
+    __shared__ u32 cnt[32], start[33], basep[32], fill[32];
     const u32 per = (a.n + gridDim.x - 1) / gridDim.x;
     const u32 lo = min(a.n, blockIdx.x * per), hi = min(a.n, lo + per);
-    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(cnt + owner_of_hash(a.hash[i], a.world), 1u);
-    __syncthreads();
-    if (threadIdx.x < a.world) {
-        basep[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(a.cursors + threadIdx.x, cnt[threadIdx.x]) : 0u;
-        if (basep[threadIdx.x] + cnt[threadIdx.x] > a.cap) a.cursors[a.world] = 1u;
-        cnt[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const u64 h = a.hash[i];
-        const u32 o = owner_of_hash(h, a.world);
-        const u32 k = basep[o] + atomicAdd(cnt + o, 1u);
-        u32 p = 0xffffffffu;
-        if (k < a.cap) {
-            p = o * a.cap + k;
-            reinterpret_cast<ulonglong2 *>(a.recv.p[o])[(size_t)a.rank * a.cap + k] = make_ulonglong2(h, a.base_index + i);
+    for (u32 tile = lo; tile < hi; tile += CK_SCAT_TILE) {
+        const u32 tn = min(hi - tile, CK_SCAT_TILE);
+        if (threadIdx.x < 32) { cnt[threadIdx.x] = 0; fill[threadIdx.x] = 0; }
+        __syncthreads();
+        u64 hreg[CK_SCAT_TILE / 256];
+        u32 oreg[CK_SCAT_TILE / 256];
+#pragma unroll
+        for (u32 k = 0; k < CK_SCAT_TILE / 256; k++) {
+            const u32 j = threadIdx.x + 256u * k;
+            if (j < tn) {
+                hreg[k] = a.hash[tile + j];
+                oreg[k] = owner_of_hash(hreg[k], a.world);
+                atomicAdd(cnt + oreg[k], 1u);
+            }
         }
-        a.pos[i] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 acc = 0;
+            for (u32 o = 0; o < a.world; o++) { start[o] = acc; acc += cnt[o]; }
+            start[a.world] = acc;
+        }
+        if (threadIdx.x < a.world) {
+            const u32 c = cnt[threadIdx.x];
+            basep[threadIdx.x] = c ? atomicAdd(a.cursors + threadIdx.x, c) : 0u;
+            if (basep[threadIdx.x] + c > a.cap) a.cursors[a.world] = 1u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (u32 k = 0; k < CK_SCAT_TILE / 256; k++) {
+            const u32 j = threadIdx.x + 256u * k;
+            if (j < tn) {
+                const u32 o = oreg[k];
+                const u32 r = atomicAdd(fill + o, 1u);
+                const u32 slot = start[o] + r;
+                stage[slot] = make_ulonglong2(hreg[k], a.base_index + tile + j);
+                own[slot] = (u8)o;
+                const u32 g = basep[o] + r;
+                a.pos[tile + j] = g < a.cap ? o * a.cap + g : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        for (u32 sl = threadIdx.x; sl < tn; sl += 256) {
+            const u32 o = own[sl];
+            const u32 g = basep[o] + (sl - start[o]);
+            if (g < a.cap) reinterpret_cast<ulonglong2 *>(a.recv.p[o])[(size_t)a.rank * a.cap + g] = stage[sl];
+        }
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(256) k_owner_pad_peers(OwnerPeerArgs a)
