@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["mono"])
     ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
     ap.add_argument("--chunks", type=int, default=1,
                     help="multi-GPU uniq: sub-batches per rank, the exchange of one overlapping the kernels of the next "
@@ -167,11 +167,112 @@ def cpu_faithful_footnote(w, seed):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_monomerize(args):
+    """`--workload mono`: `monomerize` on one GPU.  1 M concatemers (2.3 copies of a 250-400 nt unit, 1 %
+    substitutions; `--records` overrides), seed 10, min identity 0.95 (the reference CLI's default seed, its tests' identity).
+    value: resident bytes -> end indices (k_monomerize); e2e: pinned host bytes + offsets -> H2D -> kernel -> D2H of the end
+    indices; cpu_baseline: the compiled oracle port (oracle/ck_oracle.c: ck_o_monomerize_batch) on all host threads over a
+    bounded sample, whose answers are also compared with the GPU's."""
+    import numpy as np
+    import torch
+    import circkit_b200
+    from circkit_b200.monomerize import Monomerizer
+    n = args.records or 1_000_000
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    rng = np.random.default_rng(1)
+    unit_len = rng.integers(250, 401, n)
+    total_len = (unit_len * 2.3).astype(np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(total_len, out=off[1:])
+    T = int(off[-1])
+    offsets = torch.from_numpy(off).to(dev)
+    rec = torch.repeat_interleave(torch.arange(n, device=dev), torch.from_numpy(total_len).to(dev))
+    pos = torch.arange(T, device=dev) - offsets[rec]
+    h = (rec * 1000003 + (pos % torch.from_numpy(unit_len).to(dev)[rec])) * 2654435761 % 4294967296
+    letters = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    raw = letters[((h >> 13) ^ (h >> 7)) & 3]
+    g = torch.Generator(device=dev).manual_seed(7)
+    mut = torch.rand(T, device=dev, generator=g) < 0.01
+    raw[mut] = letters[torch.randint(0, 4, (int(mut.sum()),), device=dev, generator=g)]
+    del rec, pos, h, mut
+    ctx = circkit_b200.Context(max_batch_bytes=0, max_batch_records=0)
+    m = Monomerizer(10, overlap_min_identity=0.95, ctx=ctx)
+    t0 = time.time()
+    for _ in range(args.warmup):
+        out = m.end_indices_device(raw, offsets, n)
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = m.end_indices_device(raw, offsets, n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count() - launches0
+    # end to end: host buffers in, end indices out
+    h_raw = raw.cpu().pin_memory(); h_off = offsets.cpu().pin_memory()
+    h_out = torch.empty(n, dtype=torch.int32).pin_memory()
+    d_raw, d_off = torch.empty_like(raw), torch.empty_like(offsets)
+    e2e_steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        d_raw.copy_(h_raw, non_blocking=True); d_off.copy_(h_off, non_blocking=True)
+        h_out.copy_(m.end_indices_device(d_raw, d_off, n), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - te) / e2e_steps
+    clocks = sampler.stop(t0, time.time())
+    peak, src = 6551.7, "fallback"
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peak, src = float(json.load(open(pp)).get("hbm_gbs", peak)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    alg = T + 12 * n                                        # record bytes read once + offsets + the end index
+    cpu = None
+    if not args.no_cpu:
+        from oracle.monomerize import c_end_indices_batch
+        k = min(n, 200_000)
+        a_np, o_np = h_raw[: int(off[k])].numpy(), off[: k + 1].astype(np.uint64)
+        threads = os.cpu_count() or 1
+        c_end_indices_batch(a_np[: int(off[1000])], o_np[:1001], 10, None, 0.95, False, threads)
+        tc = time.perf_counter()
+        want = c_end_indices_batch(a_np, o_np, 10, None, 0.95, False, threads)
+        tc = time.perf_counter() - tc
+        same = bool((want == out[:k].cpu().numpy().astype(np.uint32)).all())
+        cpu = {"value": k / tc, "unit": "records/s", "cores": threads, "kind": "port",
+               "sample": "%d records (%.0f Mbases) of the workload, compiled oracle port (memmem seed search + byte Hamming), "
+                         "all host threads; its end indices equal the GPU's: %s" % (k, off[k] / 1e6, same)}
+        if not same:
+            raise RuntimeError("GPU and CPU port disagree on the bench sample")
+    print(json.dumps({
+        "metric": "monomerize records/sec", "value": n / (ms / 1e3), "unit": "records/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": "monomerize: %d concatemers (2.3 copies of a 250-400 nt unit, 1%% substitutions), "
+                                                    "seed 10, min identity 0.95" % n, "records_per_gpu": n,
+                                        "l2_policy": "inputs larger than L2 (%.2f GB of record bytes per step)" % (T / 1e9)},
+        "gbases_per_s": T / ms / 1e6, "clocks": clocks,
+        "e2e": {"value": n / e2e_s, "unit": "records/s", "h2d_bytes_per_step": T + 8 * (n + 1), "d2h_bytes_per_step": 4 * n,
+                "steps": e2e_steps, "api": "ck_dev_monomerize after H2D of pinned record bytes + offsets"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_monomerize (warp per record)", "achieved": alg / ms / 1e6, "peak": peak,
+                     "unit": "GB/s", "frac": alg / ms / 1e6 / peak, "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms_per_launch": ms, "launches_per_step": 1.0},
+        "cpu_baseline": cpu, "monomerized_records": int((out != -1).sum())}))
+    ctx.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "mono":
+        if rank == 0 and args.impl != "reference":
+            bench_monomerize(args)
+        return
     w = dict(WORKLOADS[args.workload])
     seed = SEEDS[args.workload]
     named = args.records == 0

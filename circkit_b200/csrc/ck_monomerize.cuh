@@ -6,10 +6,10 @@
 //   Monomerizer::last_monomer_end_index_sensitive   lib/src/monomerize.rs:127-141
 //
 // One warp per record, bytes as they are (library semantics).  first(): the seed is the last seed_len bytes; the 32 lanes
-// test 32 candidate start positions of the text seq[.. n - seed_len] at a time (bio's ShiftAnd::find_all reports every
+// test 128 candidate start positions of the text seq[.. n - seed_len] at a time (four per lane) (bio's ShiftAnd::find_all reports every
 // occurrence, overlapping ones included, by increasing start), the occurrences of a round are taken in position order and
 // the Hamming distance of prefix seq[.. occ + seed_len] against the suffix of the same length is counted by the whole
-// warp; the first occurrence within the allowed distance ends the search.  The sensitive pass runs the same code over a
+// warp (four bytes per lane and step); the first occurrence within the allowed distance ends the search.  The sensitive pass runs the same code over a
 // view that reads the monomer backwards through bio's complement table (no reverse complement is materialised).
 #pragma once
 #include "ck_device.cuh"
@@ -40,20 +40,51 @@ template <bool RC> __device__ u32 mono_first(const MonoArgs &a, MonoView<RC> v)
     const u32 s = a.seed_len, n = v.n, lane = lane_id();
     if (n <= s || n < 2 * s) return CK_MONO_NONE;          // no room for an occurrence in seq[.. n - s]
     const u32 limit = n - 2 * s + 1;                        // candidate starts 0 .. n - 2 s
-    for (u32 base = 0; base < limit; base += 32) {
-        const u32 p = base + lane;
-        bool match = p < limit;
-        for (u32 k = 0; match && k < s; k++) match = v.at(p + k) == v.at(n - s + k);
-        u32 mask = __ballot_sync(CK_FULL, match);
-        while (mask) {
-            const u32 occ = base + (u32)__ffs(mask) - 1u;
-            mask &= mask - 1u;
-            const u32 m = occ + s;                          // overlap length
-            u32 cnt = 0;
-            for (u32 t = lane; t < m; t += 32) cnt += v.at(n - m + t) != v.at(t);
-            const u64 dist = __reduce_add_sync(CK_FULL, cnt);
-            const u64 maxd = a.use_identity ? (u64)m - (u64)floor((double)m * a.identity) : a.overlap_dist;
-            if (dist <= maxd) return n - m;
+    // the first K = min(seed_len, 4) bytes of the seed as one word: a candidate start must match it before the rest of the
+    // seed is looked at (1 in 256 random positions passes instead of 1 in 4, so the divergent tail below is rare)
+    const u32 K = min(s, 4u);
+    const u32 kmask = K == 4 ? 0xffffffffu : (1u << (8 * K)) - 1u;
+    u32 seedw = 0;
+    for (u32 k = 0; k < K; k++) seedw |= v.at(n - s + k) << (8 * k);
+    // 128 candidate starts per round, four consecutive ones per lane (seven independent byte loads)
+    for (u32 base = 0; base < limit; base += 128) {
+        const u32 p0 = base + 4 * lane;
+        u32 hit = 0;
+        if (p0 < limit) {
+            u32 b[7];
+#pragma unroll
+            for (u32 k = 0; k < 7; k++) b[k] = p0 + k < n ? v.at(p0 + k) : 0u;
+#pragma unroll
+            for (u32 q = 0; q < 4; q++) {
+                const u32 w = (b[q] | (b[q + 1] << 8) | (b[q + 2] << 16) | (b[q + 3] << 24)) & kmask;
+                if (p0 + q < limit && w == seedw) hit |= 1u << q;
+            }
+        }
+        for (u32 h = hit; h; h &= h - 1) {                  // the rest of the seed for the positions that passed
+            const u32 q = (u32)__ffs(h) - 1u, p = p0 + q;
+            bool match = true;
+            for (u32 k = K; match && k < s; k++) match = v.at(p + k) == v.at(n - s + k);
+            if (!match) hit &= ~(1u << q);
+        }
+        u32 lanes = __ballot_sync(CK_FULL, hit != 0);
+        while (lanes) {                                     // occurrences in position order: by lane, then inside the lane
+            const u32 l = (u32)__ffs(lanes) - 1u;
+            lanes &= lanes - 1u;
+            u32 hq = __shfl_sync(CK_FULL, hit, l);
+            while (hq) {
+                const u32 occ = base + 4 * l + (u32)__ffs(hq) - 1u;
+                hq &= hq - 1u;
+                const u32 m = occ + s;                      // overlap length
+                u32 cnt = 0;
+                for (u32 t = 4 * lane; t < m; t += 128) {   // four bytes per lane and step
+#pragma unroll
+                    for (u32 u = 0; u < 4; u++)
+                        if (t + u < m) cnt += v.at(n - m + t + u) != v.at(t + u);
+                }
+                const u64 dist = __reduce_add_sync(CK_FULL, cnt);
+                const u64 maxd = a.use_identity ? (u64)m - (u64)floor((double)m * a.identity) : a.overlap_dist;
+                if (dist <= maxd) return n - m;
+            }
         }
     }
     return CK_MONO_NONE;

@@ -19,7 +19,9 @@
  * "everything else -> N", seq_io CR handling) are listed in DESIGN.md as
  * "parity unpinned by the reference".
  */
+#define _GNU_SOURCE          /* memmem */
 #include <stdint.h>
+#include <math.h>
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -464,4 +466,88 @@ CK_EXPORT int ck_o_max_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n < 1 ? 1 : (int)n;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * monomerize: lib/src/monomerize.rs:50-141 restated in C -- the compiled CPU baseline of
+ * tools/time_monomerize.py and a second restatement beside oracle/monomerize.py (tests/test_oracle_monomerize.py holds
+ * both to the reference's 277 unit-test vectors).  memmem stands in for bio's ShiftAnd::find_all: every occurrence of
+ * the seed in seq[.. n - seed_len], overlapping ones included, by increasing start.  NONE = SIZE_MAX.
+ * identity < 0: not set (then max distance = overlap_dist). */
+static size_t mono_first(const uint8_t *seq, size_t n, size_t s, uint64_t overlap_dist, double identity)
+{
+    if (n <= s || n < 2 * s) return SIZE_MAX;
+    const uint8_t *seed = seq + (n - s);
+    const size_t text_len = n - s;
+    size_t from = 0;
+    while (from + s <= text_len) {
+        const uint8_t *hit = (const uint8_t *)memmem(seq + from, text_len - from, seed, s);
+        if (!hit) break;
+        const size_t occ = (size_t)(hit - seq), m = occ + s;
+        const uint8_t *starter = seq + (n - m);
+        uint64_t dist = 0;
+        for (size_t t = 0; t < m; t++) dist += starter[t] != seq[t];          /* bio hamming(starter, successor) */
+        const uint64_t maxd = identity >= 0.0 ? (uint64_t)m - (uint64_t)floor((double)m * identity) : overlap_dist;
+        if (dist <= maxd) return n - m;
+        from = occ + 1;
+    }
+    return SIZE_MAX;
+}
+CK_EXPORT size_t ck_o_monomer_end(const uint8_t *seq, size_t n, size_t seed_len, uint64_t overlap_dist, double identity,
+                                  int sensitive, int first_only)
+{
+    size_t idx = mono_first(seq, n, seed_len, overlap_dist, identity);
+    if (first_only) return idx;
+    while (idx != SIZE_MAX) {                                                  /* :100-125 */
+        const size_t nxt = mono_first(seq, idx, seed_len, overlap_dist, identity);
+        if (nxt == SIZE_MAX) break;
+        idx = nxt;
+    }
+    if (sensitive) {                                                           /* :127-141 */
+        comp_init();
+        const size_t M = idx == SIZE_MAX ? n : idx;
+        uint8_t *rc = (uint8_t *)malloc(M ? M : 1);
+        for (size_t j = 0; j < M; j++) rc[j] = COMP[seq[M - 1 - j]];
+        const size_t k = mono_first(rc, M, seed_len, overlap_dist, identity);
+        free(rc);
+        if (k != SIZE_MAX) idx = M - (M - k);
+    }
+    return idx;
+}
+typedef struct {
+    const uint8_t *bytes; const uint64_t *offsets; uint64_t n_records; size_t seed_len; uint64_t overlap_dist;
+    double identity; int sensitive; uint32_t *out; atomic_ullong next;
+} mono_job;
+static void *mono_worker(void *arg)
+{
+    mono_job *j = (mono_job *)arg;
+    for (;;) {
+        const uint64_t lo = atomic_fetch_add(&j->next, 256);
+        if (lo >= j->n_records) break;
+        const uint64_t hi = lo + 256 < j->n_records ? lo + 256 : j->n_records;
+        for (uint64_t i = lo; i < hi; i++) {
+            const size_t e = ck_o_monomer_end(j->bytes + j->offsets[i], (size_t)(j->offsets[i + 1] - j->offsets[i]), j->seed_len,
+                                              j->overlap_dist, j->identity, j->sensitive, 0);
+            j->out[i] = e == SIZE_MAX ? 0xffffffffu : (uint32_t)e;
+        }
+    }
+    return NULL;
+}
+CK_EXPORT int ck_o_monomerize_batch(const uint8_t *bytes, const uint64_t *offsets, uint64_t n_records, size_t seed_len,
+                                    uint64_t overlap_dist, double identity, int sensitive, int threads, uint32_t *out_end)
+{
+    comp_init();
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    mono_job job = { bytes, offsets, n_records, seed_len, overlap_dist, identity, sensitive, out_end, 0 };
+    atomic_init(&job.next, 0);
+    if (threads == 1) { mono_worker(&job); return 0; }
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    int started = 0;
+    for (int t = 0; t < threads; t++)
+        if (pthread_create(&tid[t], NULL, mono_worker, &job) == 0) tid[started++] = tid[t];
+    if (started == 0) mono_worker(&job);
+    for (int t = 0; t < started; t++) pthread_join(tid[t], NULL);
+    free(tid);
+    return 0;
 }

@@ -86,3 +86,35 @@ class Monomerizer:
     def monomerize_sensitive(self, seq: bytes) -> bytes:
         end = self.last_monomer_end_index_sensitive(seq)
         return seq if end is None else seq[:end]
+
+
+# ---- the compiled restatement (oracle/ck_oracle.c: ck_o_monomer_end, ck_o_monomerize_batch) -------------------------------
+def c_end_index(seq: bytes, seed_len: int, overlap_dist: Optional[int] = None, overlap_min_identity: Optional[float] = None,
+                sensitive: bool = False, first_only: bool = False) -> Optional[int]:
+    import ctypes as C
+    import oracle
+    L = oracle.lib()
+    L.ck_o_monomer_end.restype = C.c_size_t
+    L.ck_o_monomer_end.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_uint64, C.c_double, C.c_int, C.c_int]
+    r = L.ck_o_monomer_end(seq, len(seq), seed_len, int(overlap_dist or 0),
+                           -1.0 if overlap_min_identity is None else float(overlap_min_identity), int(sensitive), int(first_only))
+    return None if r == C.c_size_t(-1).value else int(r)
+
+
+def c_end_indices_batch(arena, offsets, seed_len: int, overlap_dist: Optional[int] = None,
+                        overlap_min_identity: Optional[float] = None, sensitive: bool = False, threads: int = 1):
+    """numpy uint8 arena + uint64 offsets[n + 1] -> uint32[n] end indices (0xffffffff = None), `threads` host threads"""
+    import ctypes as C
+    import numpy as np
+    import oracle
+    L = oracle.lib()
+    L.ck_o_monomerize_batch.restype = C.c_int
+    L.ck_o_monomerize_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64, C.c_double, C.c_int, C.c_int,
+                                        C.c_void_p]
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.empty(len(offsets) - 1, dtype=np.uint32)
+    L.ck_o_monomerize_batch(arena.ctypes.data, offsets.ctypes.data, len(offsets) - 1, seed_len, int(overlap_dist or 0),
+                            -1.0 if overlap_min_identity is None else float(overlap_min_identity), int(sensitive), threads,
+                            out.ctypes.data)
+    return out

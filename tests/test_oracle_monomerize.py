@@ -30,6 +30,34 @@ def test_reference_unit_tests():
         assert got == k["expected"], (k["name"], k["ref"], k["seed_len"], k["overlap_dist"], k["min_identity"])
 
 
+def test_compiled_restatement_on_reference_unit_tests_and_against_the_python_one():
+    """oracle/ck_oracle.c: ck_o_monomer_end (the CPU baseline of tools/time_monomerize.py)"""
+    import numpy as np
+    from oracle.monomerize import c_end_index, c_end_indices_batch
+    for k in load_kats():
+        e = c_end_index(k["seq"], k["seed_len"], k["overlap_dist"], k["min_identity"], sensitive=k["sensitive"])
+        assert (k["seq"] if e is None else k["seq"][:e]) == k["expected"], (k["name"], k["ref"])
+    rng = random.Random(9)
+    seqs = [b"", b"A", b"ACGT" * 5]
+    for _ in range(800):
+        alpha = rng.choice([b"ACGT", b"AC", b"ACGTNRYacgtn-"])
+        unit = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 90)))
+        s = bytearray(unit * rng.randint(1, 3) + unit[: rng.randint(0, len(unit))])
+        for _ in range(rng.randint(0, 3)):
+            if s:
+                s[rng.randrange(len(s))] = rng.choice(alpha)
+        seqs.append(bytes(s))
+    for seed_len, dist, ident in ((4, 0, None), (7, 2, None), (10, None, 0.95), (1, 0, None)):
+        m = Monomerizer(seed_len, dist, ident)
+        for sens in (False, True):
+            want = [m.last_monomer_end_index_sensitive(s) if sens else m.last_monomer_end_index(s) for s in seqs]
+            off = np.zeros(len(seqs) + 1, dtype=np.uint64); np.cumsum([len(s) for s in seqs], out=off[1:])
+            got = c_end_indices_batch(np.frombuffer(b"".join(seqs), dtype=np.uint8), off, seed_len, dist, ident, sens, threads=3)
+            assert [None if g == 0xffffffff else int(g) for g in got] == want
+        assert [c_end_index(s, seed_len, dist, ident, first_only=True) for s in seqs[:200]] == \
+               [m.first_monomer_end_index(s) for s in seqs[:200]]
+
+
 def test_builder_validation():
     """lib/src/monomerize.rs:20-40 and the `validation` tests (:394-419), overlap_percentage_and_dist_panics (:479-492)"""
     for bad in (0, 64, 100):
