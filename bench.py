@@ -414,7 +414,19 @@ def main():
     padded = {"on": world > 1 and args.exchange != "exact" and w["uniq"], "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
               "peer": None}
     if padded["on"] and args.exchange == "peer" and subs is None:
-        padded["peer"] = D.PeerExchange(ctx, R, world, rank, dev)
+        # peer-mapped buffers need symmetric-memory support on the node; if any rank cannot set them up, every rank takes
+        # the same fixed-capacity buckets through NCCL instead, and the JSON line says so
+        peer, why = None, ""
+        try:
+            peer = D.PeerExchange(ctx, R, world, rank, dev)
+        except Exception as e:                              # noqa: BLE001 -- reported, not hidden
+            why = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+        okt = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()):
+            padded["peer"] = peer
+        else:
+            config["sharding"] += " [peer memory unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
     comm = torch.cuda.Stream(device=dev) if subs is not None else None
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
     if w["uniq"] and subs is None and raw_dev is None:
