@@ -562,7 +562,16 @@ def main():
 
     # ---------------- roofline of the dominant kernel (rank 0's launches)
     from circkit_b200.device import CLASS_NAMES
-    dom = max((c for c in CLASS_NAMES if ktimes[c][1]), key=lambda c: ktimes[c][0])
+    # (the small per-class launches run side by side on forked streams: the interval of a launch with no records can be as
+    # long as the kernel it waited behind, so only classes that hold records of this batch are candidates)
+    byte_ranges = {"4bit_le_2048": (1, 2048), "4bit_le_212992": (2049, 212992), "byte_le_1024": (1, 1024), "byte_le_106496": (1025, 106496)}
+
+    def holds_records(c):
+        lo_c, hi_c = D.CLASS_RANGE.get(c) or byte_ranges.get(c, (0, 0))
+        if (c in byte_ranges) != bool(w.get("raw")):
+            return False
+        return bool(((lens >= lo_c) & (lens <= hi_c)).any())
+    dom = max((c for c in CLASS_NAMES if ktimes[c][1] and holds_records(c)), key=lambda c: ktimes[c][0])
     lo_n, hi_n = D.CLASS_RANGE.get(dom, (1, 1 << 40))
     byte_lane = dom.startswith(("4bit", "byte"))
     # bytes this kernel's launch moves by the algorithm: packed read + ASCII write + 16 (+8 hash write);

@@ -100,6 +100,10 @@ struct ck_ctx {
     TableSlot *table = nullptr; u64 table_slots = 0; u64 *side = nullptr; u32 *d_overflow = nullptr;
     u64 launches = 0;
     bool attrs_set = false;
+    // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
+    // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing
+    cudaStream_t side_stream[CLS_COUNT] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[CLS_COUNT] = {};
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
     std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 3];     // [CLS_COUNT] = lane kernel, then table insert, table first
@@ -259,15 +263,15 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         ctx->launches += 2;
     }
     const u32 lane_classes = (1u << CLS_W2S) | (1u << CLS_W2M) | (1u << CLS_W2L) | (1u << CLS_W2X);
-    auto timed = [&](int slot, cudaEvent_t &e0, cudaEvent_t &e1, bool begin) -> cudaError_t {
+    auto timed = [&](int slot, cudaEvent_t &e0, cudaEvent_t &e1, bool begin, cudaStream_t on) -> cudaError_t {
         if (!ctx->timing) return cudaSuccess;
         if (begin) {
             cudaError_t e = cudaEventCreate(&e0); if (e != cudaSuccess) return e;
             e = cudaEventCreate(&e1); if (e != cudaSuccess) return e;
-            return cudaEventRecord(e0, st);
+            return cudaEventRecord(e0, on);
         }
         ctx->ev_pairs[slot].push_back(e0); ctx->ev_pairs[slot].push_back(e1);
-        return cudaEventRecord(e1, st);
+        return cudaEventRecord(e1, on);
     };
     auto base_args = [&](int c) {
         CanonArgs a{};
@@ -286,11 +290,17 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         else { a.list = sorted; a.count = io.counts + 12; a.n_direct = 0; a.min_n = 1; a.max_n = cls_max_n(CLS_W2X); }
         const int v = (a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, true));
+        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, true, st));
         s2_launch(ctx, st, a, v);
-        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, false));
+        CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, false, st));
         ctx->launches++;
     }
+    u32 to_launch = 0;
+    for (int c = 0; c < CLS_COUNT; c++)
+        if (c != CLS_HUGE && !(class_mask && !(class_mask & (1u << c)))) to_launch++;
+    const bool fork = ctx->ev_fork != nullptr && to_launch >= 2;
+    if (fork) CK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    u32 joined = 0;
     for (int c = 0; c < CLS_COUNT; c++) {
         if (c == CLS_HUGE) continue;
         if (class_mask && !(class_mask & (1u << c))) continue;
@@ -302,20 +312,28 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
         const u32 smem = kCls[c].bits ? cls_smem_bytes(c) : 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        CK_CUDA(ctx, timed(c, e0, e1, true));
+        // CTA-per-record kernels fill the GPU by themselves and keep their place on the caller's stream; the warp-per-record
+        // launches (retry lists, byte lanes, empty records) are the small ones that gain from running side by side
+        const bool side = fork && !kCls[c].cta;
+        cudaStream_t sc = side ? ctx->side_stream[c] : st;
+        if (side) CK_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        CK_CUDA(ctx, timed(c, e0, e1, true, sc));
         switch (c) {
-        case CLS_W2S: k_canon_w2<true, -1><<<grid, thr, smem, st>>>(a); break;
-        case CLS_W2M: case CLS_W2L: case CLS_W2X: k_canon_w2<false, -1><<<grid, thr, smem, st>>>(a); break;
-        case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, st>>>(a); break;
-        case CLS_W4: k_canon_warp<4><<<grid, thr, smem, st>>>(a); break;
-        case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, st>>>(a); break;
-        case CLS_W8: k_canon_warp<8><<<grid, thr, smem, st>>>(a); break;
-        case CLS_C8: k_canon_cta<8, false><<<grid, thr, smem, st>>>(a); break;
-        case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, st>>>(a); break;
+        case CLS_W2S: k_canon_w2<true, -1><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_W2M: case CLS_W2L: case CLS_W2X: k_canon_w2<false, -1><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_W4: k_canon_warp<4><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_W8: k_canon_warp<8><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_C8: k_canon_cta<8, false><<<grid, thr, smem, sc>>>(a); break;
+        case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, sc>>>(a); break;
         }
-        CK_CUDA(ctx, timed(c, e0, e1, false));
+        CK_CUDA(ctx, timed(c, e0, e1, false, sc));
+        if (side) { CK_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc)); joined |= 1u << c; }
         ctx->launches++;
     }
+    for (int c = 0; c < CLS_COUNT; c++)
+        if ((joined >> c) & 1u) CK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }
@@ -457,6 +475,11 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
         CK_INIT(cudaMemcpyToSymbol(c_mergesec, merge, sizeof(merge)));
         CK_INIT(cudaMemcpyToSymbol(c_midsec, mid, sizeof(mid)));
     }
+    CK_INIT(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int c = 0; c < CLS_COUNT; c++) {
+        CK_INIT(cudaStreamCreateWithFlags(&ctx->side_stream[c], cudaStreamNonBlocking));
+        CK_INIT(cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming));
+    }
     if (alloc_scratch(ctx, ctx->dev_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
     const u64 B = cfg->max_batch_bytes, R = cfg->max_batch_records;
     if (B || R) {
@@ -514,6 +537,11 @@ void ck_destroy(ck_ctx *ctx)
         free_scratch(s.scr);
     }
     free_scratch(ctx->dev_scr);
+    for (int c = 0; c < CLS_COUNT; c++) {
+        if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
+        if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->table) cudaFree(ctx->table);
     if (ctx->side) cudaFree(ctx->side);
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
