@@ -40,3 +40,22 @@ def test_oracle_cli_options():
         ocli.cli_monomerize(fasta, max_mismatch=1, min_identity=0.9)
     with pytest.raises(ValueError, match="between 0.0 and 1.0"):
         ocli.cli_monomerize(fasta, min_identity=1.5)
+
+
+def test_product_side_validation_needs_no_gpu():
+    """the builder's rules (lib/src/monomerize.rs:20-40) and the CLI's bail!s (src/monomerize.rs:35-45) are checked on the host
+    before anything touches the device"""
+    from circkit_b200.monomerize import Monomerizer
+    from circkit_b200 import cli
+    for bad in (0, 64):
+        with pytest.raises(ValueError, match="at least 1 and at most 63"):
+            Monomerizer(bad)
+    with pytest.raises(ValueError, match="overlap_dist and overlap_min_identity"):
+        Monomerizer(4, overlap_dist=0, overlap_min_identity=0.9)
+    with pytest.raises(ValueError, match="seed_len"):
+        Monomerizer()
+    with pytest.raises(cli.CliError, match="both max_mismatch and min_identity"):
+        cli.monomerize(b">a\nACGT\n", max_mismatch=1, min_identity=0.9)
+    with pytest.raises(cli.CliError, match="between 0.0 and 1.0"):
+        cli.monomerize(b">a\nACGT\n", min_identity=-0.1)
+    assert cli.monomerize(b"") == (b"", None) and cli.monomerize(b"\n\n", table_ext="tsv") == (b"", b"")
