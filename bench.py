@@ -264,14 +264,52 @@ def bench_monomerize(args):
     ctx.close()
 
 
+def bench_monomerize_reference(args):
+    """`--workload mono --impl reference`: the compiled oracle port of lib/src/monomerize.rs:50-141 on all host threads; each
+    step is a bounded sample (200 k records) of the same concatemer workload, generated on the host with the same law."""
+    import numpy as np
+    from oracle.monomerize import c_end_indices_batch
+    k = min(args.records or 1_000_000, 200_000)
+    rng = np.random.default_rng(1)
+    unit_len = rng.integers(250, 401, k)
+    total_len = (unit_len * 2.3).astype(np.int64)
+    off = np.zeros(k + 1, dtype=np.uint64)
+    np.cumsum(total_len, out=off[1:])
+    T = int(off[-1])
+    rec = np.repeat(np.arange(k, dtype=np.int64), total_len)
+    pos = np.arange(T, dtype=np.int64) - off[:-1].astype(np.int64)[rec]
+    h = (rec * 1000003 + (pos % unit_len[rec])) * 2654435761 % 4294967296
+    arena = np.frombuffer(b"ACGT", dtype=np.uint8)[((h >> 13) ^ (h >> 7)) & 3].copy()
+    mut = rng.random(T) < 0.01
+    arena[mut] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(mut.sum()))]
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        out = c_end_indices_batch(arena, off, 10, None, 0.95, False, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = c_end_indices_batch(arena, off, 10, None, 0.95, False, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = k / dt
+    sample = "%d records (%.0f Mbases) per step, compiled oracle port (memmem seed search + byte Hamming), %d host threads" % (k, T / 1e6, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "monomerize records/sec", "value": v, "unit": "records/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "monomerize: concatemers (2.3 copies of a 250-400 nt unit, 1% substitutions), seed 10, min identity 0.95",
+                   "records_per_step": k},
+        "cpu_baseline": {"value": v, "unit": "records/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "monomerized_records": int((out != 0xffffffff).sum())}))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "mono":
-        if rank == 0 and args.impl != "reference":
-            bench_monomerize(args)
+        if rank == 0:
+            (bench_monomerize_reference if args.impl == "reference" else bench_monomerize)(args)
         return
     w = dict(WORKLOADS[args.workload])
     seed = SEEDS[args.workload]
