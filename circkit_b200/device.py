@@ -185,7 +185,8 @@ class PeerExchange:
 
     first_index(hash64, base_index, table, out) -> state int32[world + 1]; state[world] != 0: a bucket overflowed, `out`
     is not valid and the batch must be repeated through exchange.exchange_first_index (checked by the caller, once,
-    after everything has been queued).  Every rank must call it for every batch (the barriers are collective)."""
+    after everything has been queued).  Every rank must call it for every batch (the barriers are collective), and every
+    rank must construct it with the same n_max (the bucket capacity, hence the buffer layout, derives from it)."""
 
     def __init__(self, ctx: Context, n_max: int, world: int, rank: int, dev=None, group=None):
         import torch.distributed as dist
