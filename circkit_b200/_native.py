@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CIRCKIT_B200_LIB") or os.path.join(HERE, "libcirckit_
 
 CK_OK = 0
 CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5
-CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT = 1, 2, 4
+CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_PACKED_IN = 1, 2, 4, 8
 CK_MONO_SENSITIVE, CK_MONO_FIRST_ONLY, CK_MONO_NONE = 1, 2, 0xFFFFFFFF
 CK_CLASS_2BIT_LE_512, CK_CLASS_2BIT_LE_2048, CK_CLASS_2BIT_LE_65536, CK_CLASS_2BIT_LE_425984 = 1, 2, 4, 8
 CK_CLASS_2BIT_LE_4096, CK_CLASS_2BIT_LE_8192 = 1 << 10, 1 << 11
@@ -19,6 +19,12 @@ CK_CLASS_2BIT_LE_4096, CK_CLASS_2BIT_LE_8192 = 1 << 10, 1 << 11
 class CkConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_batch_bytes", C.c_uint64),
                 ("max_batch_records", C.c_uint32), ("table_capacity", C.c_uint64)]
+
+
+class CkPackedBatch(C.Structure):
+    _fields_ = [("packed2", C.c_void_p), ("offsets", C.c_void_p), ("lens", C.c_void_p), ("lane", C.c_void_p),
+                ("lane_bytes", C.c_void_p), ("lane_offsets", C.c_void_p), ("lane_bytes_total", C.c_uint64),
+                ("n_records", C.c_uint32)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -39,6 +45,13 @@ SIGNATURES = {
     "ck_uniq_submit": (_i, [_vp, _i, _vp, _vp, _u32, _u32, _u64]),
     "ck_uniq_wait": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "ck_uniq_reset": (_i, [_vp]),
+    "ck_peer_export": (_i, [_vp, _u32, _u32, _u32, _vp]),
+    "ck_peer_attach": (_i, [_vp, _vp]),
+    "ck_dev_peer_first_index": (_i, [_vp, _vp, _vp, _u32, _u64, _vp, _u64, _vp]),
+    "ck_pack2_words": (_u64, [_u64, _u32]),
+    "ck_pack2_host": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "ck_canon_submit_packed": (_i, [_vp, _i, C.POINTER(CkPackedBatch), _u32]),
+    "ck_uniq_submit_packed": (_i, [_vp, _i, C.POINTER(CkPackedBatch), _u32, _u64]),
     "ck_lmsr_index": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "ck_lmsr": (_i, [_vp, _vp, _sz, _vp]),
     "ck_canonicalize": (_i, [_vp, _vp, _sz, _vp]),

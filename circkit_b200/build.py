@@ -19,7 +19,7 @@ def _nvcc() -> str:
 
 
 def sources() -> list[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp")))
 
 
 def stale() -> bool:
@@ -32,11 +32,15 @@ def stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "ck_lib.cu")]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
         env = dict(os.environ)
         env.pop("CC", None); env.pop("CXX", None)      # the image's CC wrapper lacks some specs
+        # the host packer (CK_F_PACKED_IN) is plain C++ with run-time-dispatched AVX2 / BMI2 paths: g++, then linked in
+        obj = os.path.join(HERE, "ck_host_pack.o")
+        subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", "-o", obj, os.path.join(CSRC, "ck_host_pack.cpp")],
+                       check=True, env=env)
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "ck_lib.cu"), obj, "-Xcompiler", "-pthread"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True, env=env)
     return LIB
 

@@ -24,6 +24,49 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
 
 
+class PackedBatch:
+    """What ck_pack2_host leaves for ck_*_submit_packed (include/circkit_b200.h, "packed host input"): the A/C/G/T
+    records at 2 bits per base in the dense host layout, normalised lengths, symbol lanes, and the bytes of the byte-lane
+    records only.  Keeps the arrays alive for as long as the batch is in flight."""
+
+    def __init__(self, offsets, dense, lens, lane, lane_bytes, lane_offsets, lane_total):
+        self.offsets, self.dense, self.lens, self.lane = offsets, dense, lens, lane
+        self.lane_bytes, self.lane_offsets, self.lane_total = lane_bytes, lane_offsets, lane_total
+        self.n = len(offsets) - 1
+        self.total = int(offsets[-1]) if len(offsets) else 0
+
+    def struct(self) -> "N.CkPackedBatch":
+        return N.CkPackedBatch(_ptr(self.dense), _ptr(self.offsets), _ptr(self.lens), _ptr(self.lane),
+                               _ptr(self.lane_bytes) if self.lane_total else None,
+                               _ptr(self.lane_offsets) if self.lane_total else None, self.lane_total, self.n)
+
+    @property
+    def h2d_bytes(self) -> int:
+        """bytes a submit copies to the device"""
+        words = (self.total >> 5) + self.n + 1
+        return 8 * words + 8 * (self.n + 1) + 5 * self.n + (self.lane_total + 8 * (self.n + 1) if self.lane_total else 0)
+
+
+def pack2_host(arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, threads: int = 0) -> PackedBatch:
+    """ck_pack2_host: the multi-threaded host packer (normalise + classify + 2-bit pack; pure host code)."""
+    lib = N.lib()
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
+    dense = np.zeros(int(lib.ck_pack2_words(total, max(n, 0))), dtype=np.uint64)
+    lens = np.zeros(max(n, 1), dtype=np.uint32)
+    lane = np.zeros(max(n, 1), dtype=np.uint8)
+    lane_bytes = np.zeros(max(total, 1), dtype=np.uint8)
+    lane_offsets = np.zeros(max(n, 0) + 1, dtype=np.uint64)
+    lane_total = C.c_uint64(0)
+    rc = lib.ck_pack2_host(_ptr(arena), _ptr(offsets), max(n, 0), N.CK_F_NORMALIZE if normalize else 0, threads, _ptr(dense),
+                           _ptr(lens), _ptr(lane), _ptr(lane_bytes), total, _ptr(lane_offsets), C.byref(lane_total))
+    if rc != N.CK_OK:
+        raise CircKitError(rc, "ck_pack2_host: bad batch (offsets not monotonic, record longer than 2^30, or null pointers)")
+    return PackedBatch(offsets, dense, lens[:max(n, 0)], lane[:max(n, 0)], lane_bytes, lane_offsets, int(lane_total.value))
+
+
 class Context:
     """One ``ck_ctx``: a device, two in-flight batch slots, the uniq first-occurrence table."""
 
@@ -122,6 +165,30 @@ class Context:
         self.canon_submit(0, arena, offsets, normalize=normalize, no_bytes=not want_bytes, aligned=aligned)
         return self.canon_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes,
                                aligned=aligned)
+
+    # -- batch API, packed host input (2 bits per base over PCIe)
+    def canon_submit_packed(self, slot: int, pb: PackedBatch, *, no_bytes=False, aligned=False):
+        flags = (N.CK_F_NO_BYTES if no_bytes else 0) | (N.CK_F_ALIGNED_OUT if aligned else 0)
+        st = pb.struct()
+        self._check(self._lib.ck_canon_submit_packed(self._h, slot, C.byref(st), flags))
+
+    def uniq_submit_packed(self, slot: int, pb: PackedBatch, base_index: int, *, no_bytes=False, aligned=False):
+        flags = (N.CK_F_NO_BYTES if no_bytes else 0) | (N.CK_F_ALIGNED_OUT if aligned else 0)
+        st = pb.struct()
+        self._check(self._lib.ck_uniq_submit_packed(self._h, slot, C.byref(st), flags, base_index))
+
+    def canonicalize_batch_packed(self, arena: np.ndarray, offsets: np.ndarray, *, normalize: bool = False, want_bytes=True,
+                                  aligned=False, threads: int = 0):
+        """canonicalize_batch through the packed host path: ck_pack2_host, then ck_canon_submit_packed / ck_canon_wait."""
+        pb = pack2_host(arena, offsets, normalize=normalize, threads=threads)
+        self.canon_submit_packed(0, pb, no_bytes=not want_bytes, aligned=aligned)
+        return self.canon_wait(0, pb.n, pb.total, want_bytes=want_bytes, aligned=aligned)
+
+    def uniq_batch_packed(self, arena: np.ndarray, offsets: np.ndarray, base_index: int = 0, *, normalize: bool = False,
+                          want_bytes=True, aligned=False, threads: int = 0):
+        pb = pack2_host(arena, offsets, normalize=normalize, threads=threads)
+        self.uniq_submit_packed(0, pb, base_index, no_bytes=not want_bytes, aligned=aligned)
+        return self.uniq_wait(0, pb.n, pb.total, want_bytes=want_bytes, aligned=aligned)
 
     def uniq_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, base_index: int, *, normalize: bool,
                     no_bytes=False, aligned=False):

@@ -54,11 +54,13 @@ __device__ __forceinline__ void stab_load()
 
 // ------------------------------------------------------------------ packed2 arena
 // 2-bit arena: A,C,G,T = 0..3, 16 bases per 32-bit unit, first base in the top bits, units in address order.  Record i
-// starts at 16-byte granule (offsets[i] >> 6) + 2 i (so every record can be streamed with aligned 128-bit loads), and
-// its units 0 .. (n >> 4) + 4 hold the bases S[b mod n], i.e. the record is followed by its own circular extension
-// (k_extend_packed2): a 16-base window that starts anywhere in the record never needs wrap logic.
-__host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec) { return 2 * ((off >> 6) + 2 * rec); }     // u64 word index
-__host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records) { return 2 * ((total >> 6) + 2 * n_records + 2); }
+// starts at 32-byte granule (offsets[i] >> 6) + 3 i, so that every record can be streamed with aligned 256-bit loads
+// (LDG.E.ENL2.256, sm_100: a lane-private 32-byte load costs one L1TEX wavefront per lane, the same as a 16-byte one), and
+// it is stored DOUBLED: units 0 .. (2 n >> 4) + 1 hold the bases S[b mod n] (k_extend_packed2 appends the second copy).
+// Every rotation of the circular record -- and the 128 + 15 bases an output round reads from it -- is then a linear
+// window of the arena: neither the scan nor the emit pass ever wraps.  The host packer only writes the first copy.
+__host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec) { return 4 * ((off >> 6) + 3 * rec); }     // u64 word index
+__host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records) { return 4 * ((total >> 6) + 3 * n_records + 3); }
 // aligned output arena (CK_F_ALIGNED_OUT): record i's canonical bytes start at byte 32 * ((offsets[i] >> 5) + i).  32 bytes =
 // one DRAM / L2 sector: a 64-byte output round of the lane kernel then covers whole sectors only (with 16-byte alignment half
 // of the records wrote half sectors at both ends of every round, which the memory system pays for with fill reads).

@@ -516,36 +516,69 @@ __global__ void k_list_starts(u32 *counts)
     }
 }
 
-// k_extend_packed2: append the circular extension to every packed record (units jn .. jn + 4, jn = n >> 4; the
-// partial unit jn keeps its real bases).  One thread per record; runs after the packer (k_prepare / k_synth_packed2).
-__global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane, u32 n_records)
+// k_extend_packed2: complete every packed record of the arena (ck_device.cuh, "packed2 arena"): units up to `last` hold
+// the bases S[b mod n], last = the unit of base 2 n + 143 (at least jn + 5, jn = n >> 4) -- the record twice, then some.
+//   dense == null : the packer (k_prepare / k_synth_packed2) wrote the first copy in place; units jn .. last are appended
+//                   (the partial unit jn keeps its real bases);
+//   dense != null : CK_F_PACKED_IN -- the host packer's dense layout (record i at 64-bit word (offsets[i] >> 5) + i, first
+//                   copy only, ck_host_pack.cpp) is spread into the arena: units 0 .. last.
+// One warp per record, one lane per destination unit; every source is a unit of the first copy (in place, unit jn is read
+// while another lane completes it: the bits a reader uses are the same before and after).
+__device__ __forceinline__ u32 p2_last_unit(u32 n) { return max((2u * n + 143u) >> 4, (n >> 4) + 5u); }
+__global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane_bits, u32 n_records,
+                                                        const u64 *dense)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_records) return;
-    if (lane && lane[i] != 2) return;
-    const u64 off = offsets[i];
-    const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
-    if (n == 0) return;
-    u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i));
-    const u32 jn = n >> 4, rem = n & 15u;
-    u32 e[5];
-    if (n >= 80) {
-        const u32 u0 = U[0], u1 = U[1], u2 = U[2], u3 = U[3], u4 = U[4], uj = U[jn];
-        const u32 sh = 32u - 2u * rem;
-        e[0] = (uj & ~(0xffffffffu >> (2 * rem))) | (u0 >> (2 * rem));
-        e[1] = __funnelshift_lc(u1, u0, sh); e[2] = __funnelshift_lc(u2, u1, sh); e[3] = __funnelshift_lc(u3, u2, sh);
-        e[4] = __funnelshift_lc(u4, u3, sh);
-    } else {
-        for (u32 k = 0; k < 5; k++) {
-            u32 v = 0;
-            for (u32 b = 0; b < 16; b++) {
-                const u32 t = (16 * (jn + k) + b) % n;
-                v = (v << 2) | ((U[t >> 4] >> (30 - 2 * (t & 15))) & 3u);
+    const u32 lane = lane_id();
+    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (u32 i = gw; i < n_records; i += nw) {
+        if (lane_bits && lane_bits[i] != 2) continue;
+        const u64 off = offsets[i];
+        const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
+        if (n == 0) continue;
+        u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i));
+        const u32 *S = dense ? reinterpret_cast<const u32 *>(dense + (off >> 5) + i) : U;
+        const u32 jn = n >> 4, last = p2_last_unit(n);
+        if (n >= 80) {
+            for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
+                const u32 r = (16u * j) % n;                          // first base of the unit, modulo n
+                const u32 q = r >> 4, sh = 2u * (r & 15u);
+                u32 w = __funnelshift_l(__ldcg(S + q + 1), __ldcg(S + q), sh);
+                if (r + 16u > n) {                                    // the seam: k bases of the tail, then the head
+                    const u32 k = n - r;
+                    w = (w & ~(0xffffffffu >> (2u * k))) | (__ldcg(S) >> (2u * k));
+                }
+                U[j] = w;
             }
-            e[k] = v;
+        } else {
+            // tiny records: base by base (at most 20 units)
+            for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
+                u32 v = 0;
+                for (u32 b = 0; b < 16; b++) {
+                    const u32 t = (16 * j + b) % n;
+                    v = (v << 2) | ((__ldcg(S + (t >> 4)) >> (30 - 2 * (t & 15))) & 3u);
+                }
+                __syncwarp(__activemask());
+                U[j] = v;
+            }
         }
+        __syncwarp();
     }
-    for (u32 k = 0; k < 5; k++) U[jn + k] = e[k];
+}
+
+// CK_F_PACKED_IN, byte-level lanes: the (normalised) bytes of the records whose lane is not 2 arrive concatenated in record
+// order; put record i's bytes at offsets[i] of the byte arena, where the byte-lane kernels look for them.
+__global__ void __launch_bounds__(256) k_scatter_lane_bytes(const u8 *lane_bytes, const u64 *lane_offsets, const u64 *offsets, const u32 *lens,
+                                                            const u8 *lane_bits, u32 n_records, u8 *bytes)
+{
+    const u32 lane = lane_id();
+    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (u32 i = gw; i < n_records; i += nw) {
+        if (lane_bits[i] == 2) continue;
+        const u8 *src = lane_bytes + lane_offsets[i];
+        u8 *dst = bytes + offsets[i];
+        const u32 n = lens[i];
+        for (u32 k = lane; k < n; k += 32) dst[k] = src[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -794,6 +827,74 @@ __global__ void __launch_bounds__(256) k_table_first_peers(FirstPeerArgs a)
         dst[k] = sl == ~0ULL ? *a.side_first : (sl == ~0ULL - 1 ? ~0ULL : a.slots[sl].first);
     }
 }
+// Barrier over the ranks of a peer group (one process per GPU, every rank's exchange block mapped into every process by
+// CUDA IPC): thread t tells rank t "rank `rank` has reached epoch e of barrier b" -- and, when `send_counts` is given, how
+// many (hash, index) pairs it has stored into rank t's receive region -- and then waits until rank t has said the same
+// here.  Launched behind the kernel whose remote stores it publishes: those stores were performed before this kernel
+// started (stream order), the system-scope fence + release store order them before the flag.  Every rank must launch it the
+// same number of times per barrier id; ranks must run on different GPUs (a rank that spins here waits for its peers' kernels).
+// Block layout (u64 words): [0, 128) flags[barrier id 0..3][src rank]; [128, 192) counts[slot 0..1][src rank].
+struct PeerBlockPtrs { u64 *p[32]; };
+#define CK_PEER_FLAG_WORDS 128u
+#define CK_PEER_HEADER_BYTES 4096u
+__global__ void k_peer_barrier(PeerBlockPtrs blocks, u32 world, u32 rank, u32 barrier_id, u64 epoch, const u32 *send_counts, u32 count_slot)
+{
+    const u32 t = threadIdx.x;
+    if (t >= world) return;
+    if (send_counts) blocks.p[t][CK_PEER_FLAG_WORDS + 32u * count_slot + rank] = send_counts[t];
+    __threadfence_system();
+    u64 *theirs = blocks.p[t] + barrier_id * 32u + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const u64 *mine = blocks.p[rank] + barrier_id * 32u + t;
+    u64 seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < epoch);
+}
+// Owner side of the fused exchange with EXACT counts (no padding, no overflow: a region holds up to `cap` = every record a
+// sender can have): insert the pairs of all regions, region s holding counts[s] of them; then answer them into the asking
+// ranks' return regions.
+struct RegionArgs {
+    TableSlot *slots; u64 mask; u64 *side_first; u32 *overflow;
+    const u64 *recv;        // local receive buffer: world regions of cap (hash, index) pairs
+    const u64 *counts;      // counts[s] (low 32 bits) = pairs in region s
+    u64 *slot_of;           // world * cap entries
+    u32 world, rank, cap;
+    PeerBlockPtrs ret;      // ret.p[s] = rank s's return buffer: world regions of cap first indices (region = owner)
+};
+__global__ void __launch_bounds__(256) k_table_insert_regions(RegionArgs a)
+{
+    const u32 s = blockIdx.y;
+    const u32 cnt = (u32)a.counts[s];
+    const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(a.recv) + (size_t)s * a.cap;
+    u64 *slot_of = a.slot_of + (size_t)s * a.cap;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        const ulonglong2 pr = pairs[k];
+        const u64 key = pr.x, idx = pr.y;
+        if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); slot_of[k] = ~0ULL; continue; }
+        u64 sl = table_home(key, a.mask);
+        u64 found = ~0ULL - 1;
+        for (u64 probes = 0; probes <= a.mask; probes++) {
+            const u64 prev = atomicCAS(&a.slots[sl].key, CK_EMPTY_KEY, key);
+            if (prev == CK_EMPTY_KEY || prev == key) { atomicMin(&a.slots[sl].first, idx); found = sl; break; }
+            sl = (sl + 1) & a.mask;
+        }
+        if (found == ~0ULL - 1) *a.overflow = 1;
+        slot_of[k] = found;
+    }
+}
+__global__ void __launch_bounds__(256) k_table_first_regions(RegionArgs a)
+{
+    const u32 s = blockIdx.y;
+    const u32 cnt = (u32)a.counts[s];
+    u64 *dst = a.ret.p[s] + (size_t)a.rank * a.cap;
+    const u64 *slot_of = a.slot_of + (size_t)s * a.cap;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        const u64 sl = slot_of[k];
+        dst[k] = sl == ~0ULL ? *a.side_first : (sl == ~0ULL - 1 ? ~0ULL : a.slots[sl].first);
+    }
+}
+
 // first_index[i] = ret[pos[i]]: the answers, which arrive in send order, back in input order
 __global__ void __launch_bounds__(256) k_gather_first(const u64 *ret, const u32 *pos, u32 n, u64 *out)
 {

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -15,6 +16,7 @@
 #include "ck_warp2.cuh"
 #include "ck_lane2.cuh"
 #include "ck_stream2.cuh"
+#include "ck_stream3.cuh"
 #include "ck_synth.cuh"
 #include "ck_monomerize.cuh"
 
@@ -80,10 +82,24 @@ struct Slot {
     u32 *d_len = nullptr; u8 *d_lane = nullptr; u8 *d_out = nullptr; u32 *d_start = nullptr;
     u8 *d_strand = nullptr; u64 *d_hash = nullptr; u64 *d_first = nullptr; u64 *d_slotof = nullptr;
     u32 *d_lists = nullptr; u32 *d_counts = nullptr;
+    u64 *d_dense = nullptr; u64 *d_laneoff = nullptr;   // CK_F_PACKED_IN: the host packer's dense 2-bit layout, byte-lane offsets
     u32 *h_counts = nullptr;            // pinned
     ExecScratch scr;
     bool busy = false, uniq = false;
     u32 n = 0, flags = 0; u64 total = 0;
+};
+
+// Multi-GPU uniq through the C ABI: this rank's exchange block (exported by CUDA IPC) and every peer's, mapped here.
+struct PeerGroup {
+    u32 world = 1, rank = 0, cap = 0;     // cap = pairs a (sender, owner) region can hold = the largest batch
+    u8 *block = nullptr; u64 block_bytes = 0, recv_bytes = 0, ret_bytes = 0;
+    void *mapped[32] = {};                // mapped[r] = rank r's block in this process (mapped[rank] == block)
+    bool exported = false, attached = false;
+    u64 epoch[4] = {};                    // launches so far per barrier id (2 * slot + phase)
+    u32 *pos[2] = {}; u32 *cursors[2] = {}; u64 *slot_of[2] = {};   // per exchange slot
+    u64 *recv(u32 r, u32 slot) const { return reinterpret_cast<u64 *>((u8 *)mapped[r] + CK_PEER_HEADER_BYTES + (u64)slot * recv_bytes); }
+    u64 *ret(u32 r, u32 slot) const { return reinterpret_cast<u64 *>((u8 *)mapped[r] + CK_PEER_HEADER_BYTES + 2 * recv_bytes + (u64)slot * ret_bytes); }
+    u64 *counts(u32 r, u32 slot) const { return reinterpret_cast<u64 *>(mapped[r]) + CK_PEER_FLAG_WORDS + 32u * slot; }
 };
 
 }  // namespace
@@ -98,8 +114,10 @@ struct ck_ctx {
     cudaEvent_t last_insert = nullptr;  // insert event of the most recently submitted uniq batch
     bool have_last_insert = false;
     TableSlot *table = nullptr; u64 table_slots = 0; u64 *side = nullptr; u32 *d_overflow = nullptr;
+    PeerGroup peer;                     // world > 1 after ck_peer_attach: uniq runs the hash-range exchange
     u64 launches = 0;
     bool attrs_set = false;
+    int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
     // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
     // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing
     cudaStream_t side_stream[CLS_COUNT] = {};
@@ -179,9 +197,20 @@ template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
     if (bytes > 48 * 1024) CK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return CK_OK;
 }
-// lane-per-record streaming kernel (ck_stream2.cuh), variant v (CK_W2_* bits)
+// lane-per-record streaming kernel, variant v (CK_W2_* bits): ck_stream3.cuh, or its predecessor ck_stream2.cuh when
+// the environment says CK_LANE_KERNEL=2 (A/B runs)
 void s2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
 {
+    if (ctx->lane_kernel != 2) {
+        const u32 g3 = 2u * (u32)ctx->num_sms, th3 = 32u * CK_S3_WARPS, sm3 = CK_S3_WARPS * CK_S3_WARP_BYTES;
+#define CK_S3(V) k_canon_s3<V><<<g3, th3, sm3, st>>>(a)
+        switch (v) {
+        case 0: CK_S3(0); break; case 1: CK_S3(1); break; case 2: CK_S3(2); break; case 3: CK_S3(3); break;
+        case 4: CK_S3(4); break; case 5: CK_S3(5); break; case 6: CK_S3(6); break; default: CK_S3(7);
+        }
+#undef CK_S3
+        return;
+    }
     const u32 g = 2u * (u32)ctx->num_sms, th = 32u * CK_S2_WARPS, sm = CK_S2_WARPS * CK_S2_WARP_BYTES;
 #define CK_S2(V) k_canon_s2<V><<<g, th, sm, st>>>(a)
     switch (v) {
@@ -202,6 +231,10 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_s2<0>, s2)) || (rc = set_smem(ctx, k_canon_s2<1>, s2)) || (rc = set_smem(ctx, k_canon_s2<2>, s2)) ||
         (rc = set_smem(ctx, k_canon_s2<3>, s2)) || (rc = set_smem(ctx, k_canon_s2<4>, s2)) || (rc = set_smem(ctx, k_canon_s2<5>, s2)) ||
         (rc = set_smem(ctx, k_canon_s2<6>, s2)) || (rc = set_smem(ctx, k_canon_s2<7>, s2))) return rc;
+    const u32 s3 = CK_S3_WARPS * CK_S3_WARP_BYTES;
+    if ((rc = set_smem(ctx, k_canon_s3<0>, s3)) || (rc = set_smem(ctx, k_canon_s3<1>, s3)) || (rc = set_smem(ctx, k_canon_s3<2>, s3)) ||
+        (rc = set_smem(ctx, k_canon_s3<3>, s3)) || (rc = set_smem(ctx, k_canon_s3<4>, s3)) || (rc = set_smem(ctx, k_canon_s3<5>, s3)) ||
+        (rc = set_smem(ctx, k_canon_s3<6>, s3)) || (rc = set_smem(ctx, k_canon_s3<7>, s3))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -215,7 +248,7 @@ struct CanonIO {
 };
 
 // sort workspace of a batch of n records: two (key, index) buffer pairs + radix-sort temporaries
-u64 lists_bytes_for(u64 n) { return 16 * (n + 4) + 24 * (n + 4) + (1ull << 20); }
+u64 lists_bytes_for(u64 n) { return ((16 * (n + 4) + 24 * (n + 4) + 255) & ~255ull) + (1ull << 20); }   // keeps what follows 256-byte aligned
 
 // classify + one launch per class.  counts[CLS_HUGE] > 0 afterwards means unprocessed records.
 int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io, u32 class_mask)
@@ -338,6 +371,9 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     return CK_OK;
 }
 
+// k_extend_packed2 runs one warp per record (8 per CTA)
+u32 extend_grid(const ck_ctx *ctx, u32 n_records) { return std::max(1u, std::min<u32>((n_records + 7) / 8, 32u * (u32)ctx->num_sms)); }
+
 u64 pow2_at_least(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
 
 int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, u32 *overflow,
@@ -360,19 +396,65 @@ int table_first(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 
     return CK_OK;
 }
 
-int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
-                  uint32_t flags, bool uniq, uint64_t base_index)
+// The hash-range exchange of multi-GPU uniq, fused into the kernels around it (replaces the single `seen` map of
+// src/uniq.rs:27 across ranks).  Per batch, on every rank, in stream order:
+//   k_owner_scatter_peers   (hash, index) pairs -> region `rank` of their OWNER's receive buffer, over NVLink
+//   k_peer_barrier (2 slot) + how many pairs went to each owner
+//   k_table_insert_regions  the owner keeps the minimum index per key
+//   [insert_done, when given, is recorded here; wait_before_query, when given, is waited for here]
+//   k_table_first_regions   first index per received pair -> region `rank` of the ASKING rank's return buffer
+//   k_peer_barrier (2 slot + 1)
+//   k_gather_first          answers back into input order
+int peer_first_index(ck_ctx *ctx, cudaStream_t st, u32 slot, const u64 *hash, u32 n, u64 base_index, TableSlot *table, u64 nslots,
+                     u64 *side, u32 *overflow, u64 *out_first, cudaEvent_t insert_done, cudaEvent_t wait_before_query)
+{
+    PeerGroup &P = ctx->peer;
+    if (!P.attached) return fail(ctx, CK_ERR_STATE, "peer group not attached");
+    if (n > P.cap) return fail(ctx, CK_ERR_ARG, "batch larger than the peer group's max_records");
+    CK_CUDA(ctx, cudaMemsetAsync(P.cursors[slot], 0, (P.world + 1) * sizeof(u32), st));
+    OwnerPeerArgs oa{};
+    oa.hash = hash; oa.n = n; oa.world = P.world; oa.rank = P.rank; oa.base_index = base_index; oa.cap = P.cap;
+    oa.cursors = P.cursors[slot]; oa.pos = P.pos[slot];
+    PeerBlockPtrs blocks{};
+    RegionArgs ra{};
+    for (u32 r = 0; r < P.world; r++) {
+        oa.recv.p[r] = P.recv(r, slot);
+        blocks.p[r] = reinterpret_cast<u64 *>(P.mapped[r]);
+        ra.ret.p[r] = P.ret(r, slot);
+    }
+    if (n) {
+        k_owner_scatter_peers<<<std::min<u32>((n + 255) / 256, 8u * (u32)ctx->num_sms), 256, 0, st>>>(oa);
+        ctx->launches++;
+    }
+    k_peer_barrier<<<1, 32, 0, st>>>(blocks, P.world, P.rank, 2 * slot, ++P.epoch[2 * slot], P.cursors[slot], slot);
+    ra.slots = table; ra.mask = nslots - 1; ra.side_first = side; ra.overflow = overflow;
+    ra.recv = P.recv(P.rank, slot); ra.counts = P.counts(P.rank, slot); ra.slot_of = P.slot_of[slot];
+    ra.world = P.world; ra.rank = P.rank; ra.cap = P.cap;
+    const u32 gx = std::max<u32>(1u, std::min<u32>((P.cap + 255) / 256, (8u * (u32)ctx->num_sms + P.world - 1) / P.world));
+    k_table_insert_regions<<<dim3(gx, P.world), 256, 0, st>>>(ra);
+    if (insert_done) CK_CUDA(ctx, cudaEventRecord(insert_done, st));
+    if (wait_before_query) CK_CUDA(ctx, cudaStreamWaitEvent(st, wait_before_query, 0));
+    k_table_first_regions<<<dim3(gx, P.world), 256, 0, st>>>(ra);
+    k_peer_barrier<<<1, 32, 0, st>>>(blocks, P.world, P.rank, 2 * slot + 1, ++P.epoch[2 * slot + 1], nullptr, 0);
+    if (n) k_gather_first<<<std::min<u32>((n + 255) / 256, 16u * (u32)ctx->num_sms), 256, 0, st>>>(P.ret(P.rank, slot), P.pos[slot], n, out_first);
+    ctx->launches += 5;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+
+// shared front of every submit: slot and batch checks.  Returns CK_OK with s.busy still false; n_records == 0 is complete.
+int submit_check(ck_ctx *ctx, int slot, const uint64_t *offsets, uint32_t n_records, uint32_t flags, bool uniq, bool have_bytes)
 {
     if (!ctx) return CK_ERR_ARG;
     if (slot < 0 || slot > 1) return fail(ctx, CK_ERR_ARG, "slot must be 0 or 1");
     Slot &s = ctx->slot[slot];
     if (s.busy) return fail(ctx, CK_ERR_STATE, "slot already holds a batch; call the matching wait first");
     if (n_records > ctx->cfg.max_batch_records) return fail(ctx, CK_ERR_ARG, "n_records exceeds max_batch_records");
-    if (n_records && (!offsets || (!bytes && offsets[n_records] != offsets[0])))
+    if (n_records && (!offsets || (!have_bytes && offsets[n_records] != offsets[0])))
         return fail(ctx, CK_ERR_ARG, "null batch pointers");
     if (uniq && !ctx->table) return fail(ctx, CK_ERR_STATE, "context was created with table_capacity 0");
     s.n = n_records; s.flags = flags; s.uniq = uniq; s.total = 0;
-    if (n_records == 0) { s.busy = true; return CK_OK; }
+    if (n_records == 0) return CK_OK;
     if (offsets[0] != 0) return fail(ctx, CK_ERR_ARG, "offsets[0] must be 0");
     const u64 total = offsets[n_records];
     if (total > ctx->cfg.max_batch_bytes) return fail(ctx, CK_ERR_ARG, "batch exceeds max_batch_bytes");
@@ -381,24 +463,34 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
         if (offsets[i + 1] - offsets[i] > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
     }
     s.total = total;
+    return CK_OK;
+}
+
+// shared back of every submit: the lane formats of the batch are in the slot (d_p2 / d_norm / d_len / d_lane); canonicalise,
+// then (uniq) the first-occurrence table, then the small result copies
+int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
+{
     cudaStream_t st = s.stream;
-    CK_CUDA(ctx, cudaSetDevice(ctx->device));
-    CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
-    PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
-    k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
-    k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records);
-    ctx->launches += 2;
+    const u32 n_records = s.n, flags = s.flags;
     CanonIO io{};
     // without normalisation every byte is a symbol: lengths are the offset differences and the lane-per-record kernel applies
-    io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = (flags & CK_F_NORMALIZE) ? s.d_len : nullptr; io.lane = s.d_lane;
+    io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = lens_given ? s.d_len : nullptr; io.lane = s.d_lane;
     io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
     int rc = run_canon(ctx, st, s.scr, io, 0);
     if (rc) return rc;
-    if (uniq) {
+    if (s.uniq && ctx->peer.attached && ctx->peer.world > 1) {
+        // multi-GPU: this batch is one of a ROUND of batches, one per rank (include/circkit_b200.h, ck_peer_attach)
+        const u32 slot = (u32)(&s - ctx->slot);
+        cudaEvent_t prev = (ctx->have_last_insert && ctx->last_insert != s.inserted) ? ctx->last_insert : nullptr;
+        rc = peer_first_index(ctx, st, slot, s.d_hash, n_records, base_index, ctx->table, ctx->table_slots, ctx->side, ctx->d_overflow,
+                              s.d_first, s.inserted, prev);
+        if (rc) return rc;
+        ctx->last_insert = s.inserted; ctx->have_last_insert = true;
+        CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts + 16, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    } else if (s.uniq) {
         rc = table_insert(ctx, st, ctx->table, ctx->table_slots, ctx->side, ctx->d_overflow, s.d_hash, nullptr,
                           base_index, n_records, s.d_slotof);
         if (rc) return rc;
@@ -415,6 +507,72 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     return CK_OK;
 }
 
+// an empty batch: nothing to do, except that in a peer group it still is this rank's part of the round (the barriers of
+// the exchange are collective)
+int submit_empty(ck_ctx *ctx, Slot &s, uint64_t base_index)
+{
+    s.busy = true;
+    if (!(s.uniq && ctx->peer.attached && ctx->peer.world > 1)) return CK_OK;
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const u32 slot = (u32)(&s - ctx->slot);
+    cudaEvent_t prev = (ctx->have_last_insert && ctx->last_insert != s.inserted) ? ctx->last_insert : nullptr;
+    int rc = peer_first_index(ctx, s.stream, slot, s.d_hash, 0, base_index, ctx->table, ctx->table_slots, ctx->side, ctx->d_overflow,
+                              s.d_first, s.inserted, prev);
+    if (rc) { s.busy = false; return rc; }
+    ctx->last_insert = s.inserted; ctx->have_last_insert = true;
+    return CK_OK;
+}
+
+int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records,
+                  uint32_t flags, bool uniq, uint64_t base_index)
+{
+    int rc = submit_check(ctx, slot, offsets, n_records, flags, uniq, bytes != nullptr);
+    if (rc) return rc;
+    Slot &s = ctx->slot[slot];
+    if (n_records == 0) return submit_empty(ctx, s, base_index);
+    const u64 total = s.total;
+    cudaStream_t st = s.stream;
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
+    PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
+    k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, nullptr);
+    ctx->launches += 2;
+    return submit_tail(ctx, s, (flags & CK_F_NORMALIZE) != 0, base_index);
+}
+
+// CK_F_PACKED_IN: the batch arrives as the host packer (ck_pack2_host) left it -- 2 bits per base for the A/C/G/T records,
+// bytes only for the others
+int submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *b, uint32_t flags, bool uniq, uint64_t base_index)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (!b) return fail(ctx, CK_ERR_ARG, "null batch");
+    const u32 n_records = b->n_records;
+    int rc = submit_check(ctx, slot, b->offsets, n_records, flags | CK_F_PACKED_IN, uniq, true);
+    if (rc) return rc;
+    Slot &s = ctx->slot[slot];
+    if (n_records == 0) return submit_empty(ctx, s, base_index);
+    if (!b->packed2 || !b->lens || !b->lane) return fail(ctx, CK_ERR_ARG, "null batch pointers");
+    if (b->lane_bytes_total && (!b->lane_bytes || !b->lane_offsets)) return fail(ctx, CK_ERR_ARG, "byte-lane records without lane_bytes / lane_offsets");
+    if (b->lane_bytes_total > ctx->cfg.max_batch_bytes) return fail(ctx, CK_ERR_ARG, "lane_bytes exceed max_batch_bytes");
+    cudaStream_t st = s.stream;
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, b->offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_len, b->lens, (size_t)n_records * 4, cudaMemcpyHostToDevice, st));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_lane, b->lane, (size_t)n_records, cudaMemcpyHostToDevice, st));
+    CK_CUDA(ctx, cudaMemcpyAsync(s.d_dense, b->packed2, (size_t)ck_pack2_words(s.total, n_records) * 8, cudaMemcpyHostToDevice, st));
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, s.d_dense);
+    ctx->launches++;
+    if (b->lane_bytes_total) {
+        CK_CUDA(ctx, cudaMemcpyAsync(s.d_laneoff, b->lane_offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, b->lane_bytes, (size_t)b->lane_bytes_total, cudaMemcpyHostToDevice, st));
+        k_scatter_lane_bytes<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_raw, s.d_laneoff, s.d_off, s.d_len, s.d_lane, n_records, s.d_norm);
+        ctx->launches++;
+    }
+    return submit_tail(ctx, s, true, base_index);
+}
+
 int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start,
                 uint8_t *out_strand, uint64_t *out_hash, uint64_t *out_first)
 {
@@ -423,7 +581,10 @@ int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *
     Slot &s = ctx->slot[slot];
     if (!s.busy || s.uniq != uniq) return fail(ctx, CK_ERR_STATE, "no matching submit on this slot");
     s.busy = false;
-    if (s.n == 0) return CK_OK;
+    if (s.n == 0) {
+        if (uniq && ctx->peer.attached && ctx->peer.world > 1) CK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        return CK_OK;
+    }
     cudaStream_t st = s.stream;
     const size_t n = s.n;
     if (out_bytes && !(s.flags & CK_F_NO_BYTES) && s.total)
@@ -443,6 +604,15 @@ int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *
 }  // namespace
 
 // =============================================================================================
+static bool table_view(void *table, u64 bytes, TableSlot *&slots, u64 &nslots, u64 *&side, u32 *&overflow)
+{
+    if (!table || bytes < 64 + sizeof(TableSlot) * 16) return false;
+    nslots = 1; while (nslots * 2 * sizeof(TableSlot) + 64 <= bytes) nslots <<= 1;
+    side = (u64 *)table; overflow = (u32 *)((u8 *)table + 8);
+    slots = (TableSlot *)((u8 *)table + 64);
+    return true;
+}
+
 extern "C" {
 
 int ck_init(const ck_config *cfg, ck_ctx **out)
@@ -453,6 +623,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     if (!ctx) return fail(nullptr, CK_ERR_ARG, "out of host memory");
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
+    if (const char *lk = getenv("CK_LANE_KERNEL")) ctx->lane_kernel = atoi(lk) == 2 ? 2 : 3;
 #define CK_INIT(call)                                                                          \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \
@@ -501,6 +672,8 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaMalloc(&s.d_slotof, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_lists, lists_bytes_for(R)));
             CK_INIT(cudaMalloc(&s.d_counts, 64 * 4));
+            CK_INIT(cudaMalloc(&s.d_dense, ((B >> 5) + R + 2) * 8));
+            CK_INIT(cudaMalloc(&s.d_laneoff, (R + 1) * 8));
             CK_INIT(cudaMallocHost(&s.h_counts, 32 * 4));
             memset(s.h_counts, 0, 32 * 4);
             if (alloc_scratch(ctx, s.scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
@@ -529,7 +702,7 @@ void ck_destroy(ck_ctx *ctx)
     for (int k = 0; k < 2; k++) {
         Slot &s = ctx->slot[k];
         void *ptrs[] = {s.d_raw, s.d_off, s.d_p2, s.d_norm, s.d_len, s.d_lane, s.d_out, s.d_start, s.d_strand,
-                        s.d_hash, s.d_first, s.d_slotof, s.d_lists, s.d_counts};
+                        s.d_hash, s.d_first, s.d_slotof, s.d_lists, s.d_counts, s.d_dense, s.d_laneoff};
         for (void *p : ptrs) if (p) cudaFree(p);
         if (s.h_counts) cudaFreeHost(s.h_counts);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -537,6 +710,12 @@ void ck_destroy(ck_ctx *ctx)
         free_scratch(s.scr);
     }
     free_scratch(ctx->dev_scr);
+    {
+        PeerGroup &P = ctx->peer;
+        for (u32 r = 0; r < P.world && P.attached; r++) if (r != P.rank && P.mapped[r]) cudaIpcCloseMemHandle(P.mapped[r]);
+        for (int k = 0; k < 2; k++) { if (P.pos[k]) cudaFree(P.pos[k]); if (P.cursors[k]) cudaFree(P.cursors[k]); if (P.slot_of[k]) cudaFree(P.slot_of[k]); }
+        if (P.block) cudaFree(P.block);
+    }
     for (int c = 0; c < CLS_COUNT; c++) {
         if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
         if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
@@ -577,6 +756,63 @@ int ck_uniq_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, u
 {
     return wait_common(ctx, slot, true, out_bytes, out_len, nullptr, nullptr, out_hash64, out_first_index);
 }
+int ck_canon_submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *batch, uint32_t flags)
+{
+    return submit_packed(ctx, slot, batch, flags, false, 0);
+}
+int ck_uniq_submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *batch, uint32_t flags, uint64_t base_index)
+{
+    return submit_packed(ctx, slot, batch, flags, true, base_index);
+}
+int ck_peer_export(ck_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_records, void *handle_out)
+{
+    if (!ctx || !handle_out || world < 1 || world > 32 || rank >= world || !max_records || (u64)world * max_records > 0xffffffffull)
+        return ctx ? fail(ctx, CK_ERR_ARG, "bad peer group arguments") : CK_ERR_ARG;
+    PeerGroup &P = ctx->peer;
+    if (P.exported) return fail(ctx, CK_ERR_STATE, "peer block already exported");
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    P.world = world; P.rank = rank; P.cap = max_records;
+    P.recv_bytes = ((u64)world * P.cap * 16 + 255) & ~255ull;
+    P.ret_bytes = ((u64)world * P.cap * 8 + 255) & ~255ull;
+    P.block_bytes = CK_PEER_HEADER_BYTES + 2 * P.recv_bytes + 2 * P.ret_bytes;
+    CK_CUDA(ctx, cudaMalloc(&P.block, P.block_bytes));
+    CK_CUDA(ctx, cudaMemset(P.block, 0, CK_PEER_HEADER_BYTES));
+    for (int k = 0; k < 2; k++) {
+        CK_CUDA(ctx, cudaMalloc(&P.pos[k], (size_t)P.cap * 4 + 16));
+        CK_CUDA(ctx, cudaMalloc(&P.cursors[k], 64 * 4));
+        CK_CUDA(ctx, cudaMalloc(&P.slot_of[k], (size_t)world * P.cap * 8 + 16));
+    }
+    CK_CUDA(ctx, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CK_CUDA(ctx, cudaIpcGetMemHandle(&h, P.block));
+    static_assert(sizeof(cudaIpcMemHandle_t) == CK_PEER_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    P.exported = true;
+    return CK_OK;
+}
+int ck_peer_attach(ck_ctx *ctx, const void *all_handles)
+{
+    if (!ctx || !all_handles) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
+    PeerGroup &P = ctx->peer;
+    if (!P.exported || P.attached) return fail(ctx, CK_ERR_STATE, "ck_peer_export first, attach once");
+    CK_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (u32 r = 0; r < P.world; r++) {
+        if (r == P.rank) { P.mapped[r] = P.block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const u8 *)all_handles + (size_t)r * CK_PEER_HANDLE_BYTES, sizeof(h));
+        CK_CUDA(ctx, cudaIpcOpenMemHandle(&P.mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    P.attached = true;
+    return CK_OK;
+}
+int ck_dev_peer_first_index(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, void *table,
+                            uint64_t table_bytes, uint64_t *out_first_index)
+{
+    TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
+    if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
+    if (n && (!hash64 || !out_first_index)) return fail(ctx, CK_ERR_ARG, "null argument");
+    return peer_first_index(ctx, (cudaStream_t)stream, 0, U(hash64), n, base_index, slots, nslots, side, ov, U(out_first_index), nullptr, nullptr);
+}
 int ck_uniq_reset(ck_ctx *ctx)
 {
     if (!ctx) return CK_ERR_ARG;
@@ -615,7 +851,7 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     if (e == cudaSuccess) {
         PrepareArgs pa{d_raw, d_off, n_records, 0u, d_p2, d_norm, d_len, d_lane};
         k_prepare<<<ctx->num_sms * 32, 256>>>(pa);
-        k_extend_packed2<<<(n_records + 255) / 256, 256>>>(d_p2, d_off, d_len, d_lane, n_records);
+        k_extend_packed2<<<extend_grid(ctx, n_records), 256>>>(d_p2, d_off, d_len, d_lane, n_records, nullptr);
         ctx->launches += 2;
         CanonIO io{};
         io.packed2 = d_p2; io.bytes = d_norm; io.offsets = d_off; io.lens = d_len; io.lane = d_lane; io.n = n_records;
@@ -706,7 +942,7 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     cudaStream_t st = (cudaStream_t)stream;
     PrepareArgs pa{bytes, U(offsets), n_records, flags & CK_F_NORMALIZE, p2, norm, out_len, lane};
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
-    k_extend_packed2<<<(n_records + 255) / 256, 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records, nullptr);
     ctx->launches += 2;
     CanonIO io{};
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
@@ -726,14 +962,6 @@ int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace)
 }
 
 uint64_t ck_dev_table_bytes(uint64_t capacity_keys) { return pow2_at_least(2 * capacity_keys + 16) * sizeof(TableSlot) + 64; }
-static bool table_view(void *table, u64 bytes, TableSlot *&slots, u64 &nslots, u64 *&side, u32 *&overflow)
-{
-    if (!table || bytes < 64 + sizeof(TableSlot) * 16) return false;
-    nslots = 1; while (nslots * 2 * sizeof(TableSlot) + 64 <= bytes) nslots <<= 1;
-    side = (u64 *)table; overflow = (u32 *)((u8 *)table + 8);
-    slots = (TableSlot *)((u8 *)table + 64);
-    return true;
-}
 int ck_dev_table_clear(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes)
 {
     TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
@@ -941,7 +1169,7 @@ int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_in
     SynthArgs a{seed, n_records, 0, 0, 0, dup_permille, adversarial_permille, first_index};
     if (n_records) {
         k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev));
-        k_extend_packed2<<<(n_records + 255) / 256, 256, 0, (cudaStream_t)stream>>>(U(packed2_dev), U(offsets_dev), nullptr, nullptr, n_records);
+        k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, (cudaStream_t)stream>>>(U(packed2_dev), U(offsets_dev), nullptr, nullptr, n_records, nullptr);
     }
     ctx->launches += 2;
     CK_CUDA(ctx, cudaGetLastError());

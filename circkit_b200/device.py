@@ -56,7 +56,7 @@ def synth_batch(ctx: Context, *, seed: int, first_index: int, n_records: int, ki
     total = C.c_uint64(0)
     ctx._check(ctx._lib.ck_synth_offsets(ctx.handle, _stream(), seed, first_index, n_records, kind, lo, hi,
                                          dup_permille, _p(offsets), C.byref(total)))
-    words = 2 * ((total.value >> 6) + 2 * n_records + 2)       # ck_device.cuh: p2_words
+    words = 4 * ((total.value >> 6) + 3 * n_records + 3)       # ck_device.cuh: p2_words
     packed2 = torch.empty(words, dtype=torch.int64, device=dev)
     ctx._check(ctx._lib.ck_synth_packed2(ctx.handle, _stream(), seed, first_index, n_records, _p(offsets),
                                          dup_permille, adversarial_permille, _p(packed2)))

@@ -51,6 +51,8 @@ extern "C" {
                                each record from its aligned start (it copies record by record anyway:
                                src/canonicalize.rs:33-37). */
 
+#define CK_F_PACKED_IN 8u   /* (set by the *_submit_packed entries) the batch came through ck_pack2_host */
+
 typedef struct ck_ctx ck_ctx;
 
 typedef struct ck_config {
@@ -86,6 +88,57 @@ int ck_uniq_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, u
                  uint64_t *out_first_index);
 int ck_uniq_reset(ck_ctx *ctx);   /* forget every key (new input file) */
 
+/* ---- packed host input: 2 bits per base over PCIe instead of 8 -----------------------------------
+ * The host side the reference keeps (FASTA reader threads, src/uniq.rs:29-41) packs while it parses: ck_pack2_host applies
+ * needletail's normalisation when flags has CK_F_NORMALIZE (else bytes as they are), decides every record's symbol lane
+ * and writes
+ *   packed2_dense  the A/C/G/T records, 16 bases per 32-bit unit (first base in the top bits, units in address order), record i
+ *                  at 64-bit word (offsets[i] >> 5) + i; ck_pack2_words(total, n) words in all;
+ *   lens[i]        normalised length;   lane[i] = 2 (packed), 4 or 8 (bits per symbol of the byte-level lanes);
+ *   lane_bytes     the normalised bytes of the records with lane != 2, concatenated in record order; lane_offsets[n + 1]
+ *                  = where each starts (all zero when there are none); *lane_bytes_total = their sum.
+ * `threads` host threads share the batch (0 = all hardware threads).  Pure host code: no context, no CUDA call.  The
+ * result is what ck_canon_submit_packed / ck_uniq_submit_packed take (they copy lens, lane and the dense words -- a
+ * quarter of the ASCII bytes -- and spread the records into the device arena themselves); everything else, including the
+ * waits and the output layout (same `offsets`), is as for ck_canon_submit / ck_uniq_submit. */
+typedef struct ck_packed_batch {
+    const uint64_t *packed2;      /* ck_pack2_words(offsets[n_records], n_records) words, pinned for speed */
+    const uint64_t *offsets;      /* n_records + 1 raw symbol offsets, offsets[0] == 0 */
+    const uint32_t *lens;         /* n_records */
+    const uint8_t *lane;          /* n_records */
+    const uint8_t *lane_bytes;    /* may be NULL when lane_bytes_total == 0 */
+    const uint64_t *lane_offsets; /* n_records + 1; may be NULL when lane_bytes_total == 0 */
+    uint64_t lane_bytes_total;
+    uint32_t n_records;
+} ck_packed_batch;
+uint64_t ck_pack2_words(uint64_t total_bytes, uint32_t n_records);
+int ck_pack2_host(const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records, uint32_t flags, uint32_t threads,
+                  uint64_t *packed2_dense, uint32_t *lens, uint8_t *lane, uint8_t *lane_bytes, uint64_t lane_bytes_capacity,
+                  uint64_t *lane_offsets, uint64_t *lane_bytes_total);
+int ck_canon_submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *batch, uint32_t flags);
+int ck_uniq_submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *batch, uint32_t flags, uint64_t base_index);
+
+/* ---- multi-GPU uniq: one `seen` map (src/uniq.rs:27) over several GPUs of one NVLink / NVSwitch node ----------------
+ * One process and one context per GPU.  Keys are owned by hash range (owner = floor(hash64 * world / 2^64)); the
+ * (hash64, index) pairs of a batch are stored straight into their owners' buffers by the partition kernel, the owners keep
+ * the minimum index per key and store the answers straight back -- device-side barriers, no collective, no host
+ * synchronisation.  Setup, once:
+ *   ck_peer_export   allocates this rank's exchange block for batches of up to max_records records and writes its CUDA IPC
+ *                    handle (CK_PEER_HANDLE_BYTES bytes) to handle_out;
+ *   (the host exchanges the handles by any means: a file, a pipe, MPI, any process group)
+ *   ck_peer_attach   all_handles = the world handles in rank order; maps every peer's block.
+ * Afterwards ck_uniq_submit / ck_uniq_submit_packed on this context are COLLECTIVE: the ranks submit in rounds -- in round j
+ * every rank submits exactly one batch (possibly with 0 records) on the same slot -- and every index of round j must be larger
+ * than every index of round j - 1 (e.g. batch k of the input goes to rank k mod world in round k / world, with base_index =
+ * the batch's position in the input).  out_first_index then is exact at ck_uniq_wait, as on one GPU: the first occurrence over
+ * everything submitted to ANY rank so far.  The table of each context (table_capacity) holds the keys this rank owns.
+ * ck_dev_peer_first_index is the same exchange for device-resident hashes (one collective call per rank, any stream). */
+#define CK_PEER_HANDLE_BYTES 64
+int ck_peer_export(ck_ctx *ctx, uint32_t world, uint32_t rank, uint32_t max_records, void *handle_out);
+int ck_peer_attach(ck_ctx *ctx, const void *all_handles);
+int ck_dev_peer_first_index(ck_ctx *ctx, void *stream, const uint64_t *hash64, uint32_t n, uint64_t base_index, void *table,
+                            uint64_t table_bytes, uint64_t *out_first_index);
+
 /* ---- library drop-ins (single record, library semantics: no normalisation) -------------------
  * lib/src/canonicalize.rs:5,41,54.  These run the same device kernels on a batch of one. */
 int ck_lmsr_index(ck_ctx *ctx, const uint8_t *s, size_t n, size_t *out_index);
@@ -99,9 +152,10 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
  * All pointers are device pointers, `stream` is a cudaStream_t (0 = default stream).  Nothing is copied
  * and nothing synchronises; call ck_dev_check() once a stream's work matters.
  * packed2: 2-bit arena, A,C,G,T = 0..3, 16 bases per 32-bit unit with the first base in the top bits, units in
- * address order; record i starts at byte 16 * ((offsets[i] >> 6) + 2 i) and is followed by its own circular extension
- * (units 0 .. (n >> 4) + 4 hold the bases S[b mod n]); the arena holds 2 * (total/64 + 2 n_records + 2) 64-bit words.  class_mask: 0 = any record; else a promise about the batch (bit c set =
- * length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
+ * address order; record i starts at byte 32 * ((offsets[i] >> 6) + 3 i) and is stored DOUBLED (units 0 .. (2 n + 143) >> 4,
+ * at least (n >> 4) + 5, hold the bases S[b mod n]), so that every rotation of the circular record is a linear window;
+ * the arena holds 4 * (total/64 + 3 n_records + 3) 64-bit words.  class_mask: 0 = any record; else a promise about the
+ * batch (bit c set = length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
  * records outside the promise are reported by ck_dev_check(), never silently dropped. */
 #define CK_CLASS_2BIT_LE_512 (1u << 0)
 #define CK_CLASS_2BIT_LE_2048 (1u << 1)

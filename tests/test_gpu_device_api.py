@@ -95,9 +95,9 @@ def test_lane_kernel_variants(env, want_bytes, want_hash, lo, hi, mask_extra):
         assert np.array_equal(arena[src], want["out"])
 
 
-def test_packed_arena_carries_its_circular_extension(env):
-    """Format of the packed arena (ck_device.cuh): record i at 16-byte granule (offsets[i] >> 6) + 2 i, units
-    0 .. (n >> 4) + 4 hold S[b mod n]."""
+def test_packed_arena_holds_every_record_doubled(env):
+    """Format of the packed arena (ck_device.cuh): record i at 32-byte granule (offsets[i] >> 6) + 3 i, units
+    0 .. max((2 n + 143) >> 4, (n >> 4) + 5) hold S[b mod n] (the record twice, then some)."""
     ctx, D, torch = env
     n = 300
     b = D.synth_batch(ctx, seed=5, first_index=0, n_records=n, kind=0, lo=1, hi=700)
@@ -107,8 +107,8 @@ def test_packed_arena_carries_its_circular_extension(env):
     code = {65: 0, 67: 1, 71: 2, 84: 3}
     for i in list(range(40)) + [n - 1]:
         L = int(off[i + 1] - off[i])
-        g = (int(off[i]) >> 6) + 2 * i
-        units = words[4 * g: 4 * g + (L >> 4) + 5]
+        g = (int(off[i]) >> 6) + 3 * i
+        units = words[8 * g: 8 * g + max((2 * L + 143) >> 4, (L >> 4) + 5) + 1]
         seq = [code[int(c)] for c in ascii_[off[i]: off[i + 1]]]
         for j, u in enumerate(units):
             want = 0
