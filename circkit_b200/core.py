@@ -215,6 +215,18 @@ class Context:
         return self.uniq_wait(0, len(offsets) - 1, int(offsets[-1]) if len(offsets) else 0, want_bytes=want_bytes,
                               aligned=aligned)
 
+    # -- multi-GPU uniq (one process and one context per GPU; include/circkit_b200.h, "multi-GPU uniq")
+    def peer_export(self, world: int, rank: int, max_records: int) -> bytes:
+        """allocate this rank's exchange block, return its CUDA IPC handle (give every rank the list of all of them)"""
+        h = C.create_string_buffer(N.CK_PEER_HANDLE_BYTES)
+        self._check(self._lib.ck_peer_export(self._h, world, rank, max_records, h))
+        return h.raw
+
+    def peer_attach(self, handles: "list[bytes]"):
+        """map every rank's exchange block (handles in rank order); afterwards uniq submits are collective rounds"""
+        blob = b"".join(handles)
+        self._check(self._lib.ck_peer_attach(self._h, blob))
+
     def uniq_reset(self):
         self._check(self._lib.ck_uniq_reset(self._h))
 

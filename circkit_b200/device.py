@@ -222,6 +222,26 @@ class PeerExchange:
         return self.state
 
 
+class PeerGroup:
+    """The same fused exchange through the library's own peer group (ck_peer_export / ck_peer_attach, CUDA IPC): exact
+    per-owner counts travel with the first barrier, so there is no padding, no overflow and no fallback, and nothing here
+    needs torch beyond the process group that carries the 64-byte handles.  Every rank constructs it with the same n_max
+    and calls first_index() for every batch (the barriers are collective)."""
+
+    def __init__(self, ctx: Context, n_max: int, world: int, rank: int, group=None):
+        import torch.distributed as dist
+        self.ctx, self.world, self.rank = ctx, world, rank
+        mine = ctx.peer_export(world, rank, n_max)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        ctx.peer_attach(handles)
+
+    def first_index(self, hash64: torch.Tensor, base_index: int, table: "DeviceTable", out: torch.Tensor):
+        n = hash64.numel()
+        self.ctx._check(self.ctx._lib.ck_dev_peer_first_index(self.ctx.handle, _stream(), _p(hash64), n, base_index, _p(table.buf),
+                                                              table.bytes, _p(out)))
+
+
 def exchange_bucket_capacity(n: int, world: int) -> int:
     mean = n / world
     return int(mean + 8.0 * (mean ** 0.5) + 64) + 1
