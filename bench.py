@@ -50,14 +50,13 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["mono"])
     ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
-    ap.add_argument("--chunks", type=int, default=1,
-                    help="multi-GPU uniq: sub-batches per rank, the exchange of one overlapping the kernels of the next "
-                         "(measured at 2 GPUs: 2 or 4 sub-batches are slower than 1 -- smaller launches, more collectives)")
+    ap.add_argument("--no-config5", action="store_true", help="default workload only: skip the 100 M-record config-5 sub-record")
+    ap.add_argument("--c5-records", type=int, default=100_000_000, help="records of the config-5 sub-record, split over the GPUs")
     ap.add_argument("--overlap", action="store_true",
                     help="uniq: run the table / exchange stage of a step on a second stream with double-buffered outputs, so that "
                          "it overlaps the canonicalisation of the next step (measured: +3-7 % on config 2, but the table's random "
                          "atomics can halve the speed of the latency-bound lane kernel on config 5, so it is off by default)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "padded", "exact"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "symm", "padded", "exact"],
                     help="multi-GPU uniq, how (hash, index) pairs reach their owner: peer = stored straight into the owner's buffer by "
                          "the partition kernel over NVLink (fixed-capacity buckets, device-side barriers, no collective); padded = "
                          "the same buckets through one equal-split NCCL all-to-all each way; exact = per-owner counts exchanged first "
@@ -302,75 +301,278 @@ def bench_monomerize_reference(args):
         "monomerized_records": int((out != 0xffffffff).sum())}))
 
 
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload == "mono":
-        if rank == 0:
-            (bench_monomerize_reference if args.impl == "reference" else bench_monomerize)(args)
-        return
-    w = dict(WORKLOADS[args.workload])
-    seed = SEEDS[args.workload]
-    named = args.records == 0
-    if args.records:
-        w["records"] = args.records
-    metric = "canonicalize+uniq records/sec" if w["uniq"] else "canonicalize records/sec"
-    config = {"workload": w["desc"] + ("" if named else " [REDUCED: --records %d, not the named config]" % w["records"]),
-              "records_per_gpu": w["records"], "length_law": ["uniform", "log-uniform"][w["kind"]],
-              "length_range": [w["lo"], w["hi"]], "duplicate_fraction": w["dup"] / 1000.0,
-              "l2_policy": "inputs larger than L2 (packed arena + ASCII output per step >> 126 MB)",
-              "sharding": "contiguous input-index ranges per GPU; uniq keys owned by hash range, exchange: " +
-                          {"peer": "partition / query kernels store into the peers' buffers over NVLink, device-side barriers",
-                           "padded": "fixed-capacity buckets, equal-split NCCL all-to-all",
-                           "exact": "counts, then NCCL all-to-all"}[args.exchange]}
+def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_first, sync_all, steps):
+    """The same metric end to end through the host-buffer C ABI, copies and host packing inside the timed region:
+    pinned ASCII record bytes -> ck_pack2_host (normalise + classify + 2-bit pack, all host threads of this rank) ->
+    ck_uniq_submit_packed / ck_canon_submit_packed (H2D of a quarter of the bytes, kernels) -> ck_*_wait (D2H of the results).
+    Batches alternate between the two slots, so packing, copies and kernels of consecutive batches overlap.
+    world > 1: GLOBAL uniq through the library's peer group (ck_peer_export / ck_peer_attach): batch k of the input goes to
+    rank k % world in round k // world, every round is one collective exchange, first indices are exact at every wait."""
+    import ctypes as C
+    import numpy as np
+    from circkit_b200 import _native as N
+    lib = ctx._lib
+    seed = SEEDS[wname]
+    uniq = w["uniq"]
+    raw = bool(w.get("raw"))
+    RB = 1 << 17 if w["hi"] > 1000 else 1 << 19          # records per batch (<= max_batch_records, bytes <= max_batch_bytes)
+    if w["hi"] > 50_000:
+        RB = 1 << 11
+    total_records = R * world
+    n_batches = (total_records + RB - 1) // RB
+    mine = list(range(rank, n_batches, world))             # this rank's batches of the global input
+    rounds = (n_batches + world - 1) // world
+    # every rank pins its own input: bound it to ~4 GiB of record bytes per rank when there are several (the first rounds of
+    # the input -- the same steady-state batches, fewer of them; first indices of a prefix are those of the whole run)
+    mean_len = (w["lo"] + w["hi"]) / 2 if w["kind"] == 0 else (w["hi"] - w["lo"]) / np.log(w["hi"] / w["lo"])
+    if world > 1:
+        rounds = max(1, min(rounds, int((4 << 30) / (RB * mean_len))))
+    mine = [k for k in mine if k // world < rounds]
+    if world > 1 and uniq and not getattr(ctx, "_peer_attached", False):
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export(world, rank, ctx.max_batch_records))
+        ctx.peer_attach(handles)
+        ctx._peer_attached = True
+    threads = max(1, (os.cpu_count() or 1) // world)
+    # ---- this rank's batches as pinned ASCII + offsets
+    batches = []
+    for k in mine:
+        lo_i = k * RB
+        n_k = min(RB, total_records - lo_i)
+        if raw:
+            from circkit_b200 import synth_host
+            a_np, o_np = synth_host.make_iupac_records(n_k, w["lo"], w["hi"], seed + 1000 + k)
+            tot = int(o_np[-1])
+            hp = lib.ck_alloc_pinned(ctx.handle, tot + 64)
+            hb = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(tot + 64,))
+            hb[:tot] = a_np
+            off = o_np.astype(np.uint64)
+        else:
+            b = D.synth_batch(ctx, seed=seed, first_index=lo_i, n_records=n_k, kind=w["kind"], lo=w["lo"], hi=w["hi"],
+                              dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
+            asc = D.unpack_ascii(ctx, b)
+            tot = b.total
+            hp = lib.ck_alloc_pinned(ctx.handle, tot + 64)
+            hb = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(tot + 64,))
+            torch.from_numpy(hb)[:tot].copy_(asc)
+            off = b.offsets.cpu().numpy().astype(np.uint64)
+            del b, asc
+        op = lib.ck_alloc_pinned(ctx.handle, off.nbytes)
+        oarr = np.ctypeslib.as_array(C.cast(op, C.POINTER(C.c_uint64)), shape=(len(off),))
+        oarr[:] = off
+        batches.append(dict(k=k, lo=lo_i, n=n_k, total=tot, bytes_p=hp, off=oarr, off_p=op))
+    torch.cuda.synchronize()
+    max_total = max([b["total"] for b in batches] + [1])
+    max_n = max([b["n"] for b in batches] + [1])
+    # ---- three packed staging sets (pinned): dense words, lens, lanes, byte-lane bytes + offsets
+    sets = []
+    for _ in range(3):
+        words = int(lib.ck_pack2_words(max_total, max_n))
+        s = dict(dense=lib.ck_alloc_pinned(ctx.handle, 8 * words), lens=lib.ck_alloc_pinned(ctx.handle, 4 * max_n + 16),
+                 lane=lib.ck_alloc_pinned(ctx.handle, max_n + 16), lane_off=lib.ck_alloc_pinned(ctx.handle, 8 * (max_n + 1)),
+                 lane_bytes=lib.ck_alloc_pinned(ctx.handle, (max_total if raw else (1 << 20)) + 64),
+                 lane_cap=(max_total if raw else (1 << 20)), total=C.c_uint64(0), st=None)
+        sets.append(s)
+    n_mine = sum(b["n"] for b in batches)
+    out_first_p = lib.ck_alloc_pinned(ctx.handle, 8 * (n_mine + 1))
+    out_hash_p = lib.ck_alloc_pinned(ctx.handle, 8 * (n_mine + 1))
+    out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (n_mine + 1))
+    out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (n_mine + 1))
+    out_strand_p = lib.ck_alloc_pinned(ctx.handle, (n_mine + 1))
+    pos = [0]
+    for b in batches:
+        pos.append(pos[-1] + b["n"])
+    # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record (config 3: + CK_F_NORMALIZE)
+    sub_flags = 2
+    pack_flags = 1 if raw else 0
+    stats = dict(pack_s=0.0, h2d=0)
 
-    # ---------------- reference arm: the CPU path, rank 0 only
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        r = cpu_arm(w, seed, max(args.cpu_seconds, 4.0 * (args.steps + args.warmup)), args.steps, args.warmup, w["uniq"])
-        sample = ("oracle port of circKit's path (Duval x2 + revcomp + compare, xxh3, keep-first map; O(1) byte "
-                  "indexing -- conservative: the reference's chars().nth(i) is O(i)); %d records / %.1f Mbases of the "
-                  "workload per step, worker stage on %d threads, consumer stage serial, step = max of the two"
-                  % (r["sample_records"], r["sample_bases"] / 1e6, r["cores"]))
-        line = {"impl": "reference", "metric": metric, "value": r["records_per_s"], "unit": "records/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": config, "gbases_per_s": r["gbases_per_s"],
-                "cpu_baseline": {"value": r["records_per_s"], "unit": "records/s", "cores": r["cores"], "kind": "port",
-                                 "sample": sample},
-                "e2e": {"value": r["records_per_s"], "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return
+    def pack(i):
+        b, s = batches[i], sets[i % 3]
+        t0 = time.perf_counter()
+        rc = lib.ck_pack2_host(b["bytes_p"], b["off_p"], b["n"], pack_flags, threads, s["dense"], s["lens"], s["lane"], s["lane_bytes"],
+                               s["lane_cap"], s["lane_off"], C.byref(s["total"]))
+        stats["pack_s"] += time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError("ck_pack2_host failed: %d" % rc)
+        lt = int(s["total"].value)
+        s["st"] = N.CkPackedBatch(s["dense"], b["off_p"], s["lens"], s["lane"], s["lane_bytes"] if lt else None,
+                                  s["lane_off"] if lt else None, lt, b["n"])
+        stats["h2d"] += 8 * int(lib.ck_pack2_words(b["total"], b["n"])) + 8 * (b["n"] + 1) + 5 * b["n"] + (lt + 8 * (b["n"] + 1) if lt else 0)
 
-    # ---------------- B200 arm
+    empty = N.CkPackedBatch(None, None, None, None, None, None, 0, 0)
+
+    def submit(j):                                        # round j: this rank's batch, or an empty one (the rounds are collective)
+        i = j if world == 1 else j
+        if i < len(batches):
+            b, s = batches[i], sets[i % 3]
+            if uniq:
+                ctx._check(lib.ck_uniq_submit_packed(ctx.handle, j & 1, C.byref(s["st"]), sub_flags, b["lo"]))
+            else:
+                ctx._check(lib.ck_canon_submit_packed(ctx.handle, j & 1, C.byref(s["st"]), sub_flags))
+        else:
+            ctx._check(lib.ck_uniq_submit_packed(ctx.handle, j & 1, C.byref(empty), sub_flags, 0))
+
+    def wait(j):
+        if j < len(batches):
+            c0 = pos[j]
+            if uniq:
+                ctx._check(lib.ck_uniq_wait(ctx.handle, j & 1, None, out_len_p + 4 * c0, out_hash_p + 8 * c0, out_first_p + 8 * c0))
+            else:
+                ctx._check(lib.ck_canon_wait(ctx.handle, j & 1, None, out_len_p + 4 * c0, out_start_p + 4 * c0, out_strand_p + c0, None))
+        else:
+            ctx._check(lib.ck_uniq_wait(ctx.handle, j & 1, None, None, None, None))
+
+    n_rounds = rounds if (world > 1 and uniq) else len(batches)
+
+    def e2e_step():
+        if uniq:
+            ctx.uniq_reset()
+            if world > 1:
+                dist.barrier()
+        stats["pack_s"], stats["h2d"] = 0.0, 0
+        if batches:
+            pack(0)
+        for j in range(n_rounds):
+            submit(j)
+            if j + 1 < len(batches):
+                pack(j + 1)                                # the host packs the next batch while the device works on this one
+            if j >= 1:
+                wait(j - 1)
+        if n_rounds:
+            wait(n_rounds - 1)
+
+    e2e_step()                         # warm-up
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    # ---- parity: first indices of the e2e run == the resident run's (global when world > 1)
+    parity = None
+    if uniq:
+        got = np.ctypeslib.as_array(C.cast(out_first_p, C.POINTER(C.c_uint64)), shape=(max(n_mine, 1),))[:n_mine]
+        if world > 1:
+            allf = [torch.empty(R, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(allf, resident_first[:R].contiguous())
+            want_all = torch.cat(allf).cpu().numpy().astype(np.uint64)
+        else:
+            want_all = resident_first[:R].cpu().numpy().astype(np.uint64)
+        ok = True
+        for i, b in enumerate(batches):
+            ok = ok and bool(np.array_equal(got[pos[i]: pos[i + 1]], want_all[b["lo"]: b["lo"] + b["n"]]))
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = bool(int(flag.item()))
+        if not parity:
+            raise RuntimeError("e2e first_index != resident first_index")
+    cnt = torch.tensor([n_mine, sum(b["total"] for b in batches), stats["h2d"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+    rec_step, bases_step, h2d = int(cnt[0].item()), int(cnt[1].item()), int(cnt[2].item())
+    d2h = rec_step * ((8 + 8 + 4) if uniq else (4 + 4 + 1))
+    e2e = {"value": rec_step / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "batches_per_step": len(batches) if world == 1 else n_batches if rounds * world >= n_batches else rounds * world,
+           "records_per_batch": RB,
+           "api": ("ck_pack2_host + ck_uniq_submit_packed / ck_uniq_wait" if uniq else "ck_pack2_host + ck_canon_submit_packed / ck_canon_wait")
+                  + (" over a peer group (ck_peer_export / ck_peer_attach): global first indices" if world > 1 and uniq else ""),
+           "input": "ASCII record bytes + offsets in pinned host memory; the host packer (%d threads per rank) runs INSIDE the timed region" % threads,
+           "result": "first_index + hash64 + length per record" if uniq else "start + strand + length per record",
+           "gbases_per_s": bases_step / (dt / e2e_steps) / 1e9, "records_per_step": rec_step,
+           "host_pack_seconds_per_step_rank0": stats["pack_s"], "first_index_parity_with_resident_run": parity,
+           "note": ("every rank pins its share of the input: the first %d rounds (%d records) of the %d-record input; global uniq over that prefix"
+                    % (rounds, rec_step, total_records)) if world > 1 and rec_step < total_records else ""}
+    for b in batches:
+        lib.ck_free_pinned(ctx.handle, b["bytes_p"]); lib.ck_free_pinned(ctx.handle, b["off_p"])
+    for s in sets:
+        for key in ("dense", "lens", "lane", "lane_off", "lane_bytes"):
+            lib.ck_free_pinned(ctx.handle, s[key])
+    for p in (out_first_p, out_hash_p, out_len_p, out_start_p, out_strand_p):
+        lib.ck_free_pinned(ctx.handle, p)
+    return e2e
+
+
+SHARDING = {"peer": "partition / query kernels store into the peers' buffers over NVLink (CUDA IPC peer group of the C library, exact counts, device-side barriers)",
+            "symm": "the same fused kernels over torch symmetric memory, fixed-capacity buckets",
+            "padded": "fixed-capacity buckets, equal-split NCCL all-to-all",
+            "exact": "counts, then NCCL all-to-all"}
+
+
+def make_config(args, w, R, named):
+    """`config` of the JSON line: the same dict for the B200 arm and the reference arm"""
+    return {"workload": w["desc"] + ("" if named else " [REDUCED: %d records per GPU, not the named config]" % R),
+            "records_per_gpu": R, "length_law": ["uniform", "log-uniform"][w["kind"]],
+            "length_range": [w["lo"], w["hi"]], "duplicate_fraction": w["dup"] / 1000.0,
+            "l2_policy": "inputs larger than L2 (packed arena + ASCII output per step >> 126 MB)",
+            "sharding": "contiguous input-index ranges per GPU; uniq keys owned by hash range, exchange: " + SHARDING[args.exchange]}
+
+
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def global_first_index_check(ctx, D, torch, dist, dev, rank, world, R, hash_local, first_local):
+    """Multi-rank parity of uniq (src/uniq.rs:42-78: ONE `seen` map over the whole input): every rank's hashes and the
+    first indices the fused exchange gave it are gathered on rank 0, which rebuilds the global first-occurrence index with the
+    single-GPU table (ck_dev_table_insert / ck_dev_table_first -- the path the oracle tests pin) over all world * R keys in
+    input order and compares.  -> (parity ok, global unique records) on rank 0, (None, None) elsewhere."""
+    hs = [torch.empty(R, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+    fs = [torch.empty(R, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(hash_local[:R].contiguous(), hs, dst=0)
+    dist.gather(first_local[:R].contiguous(), fs, dst=0)
+    if rank != 0:
+        return None, None
+    table = D.DeviceTable(ctx, capacity_keys=int(R * world * 1.05) + 1024, dev=dev)
+    slots = [torch.empty(R, dtype=torch.int64, device=dev) for _ in range(world)]
+    for r in range(world):
+        table.insert(hs[r], R, slots[r], base_index=r * R)
+    ok, uniq = True, 0
+    want = torch.empty(R, dtype=torch.int64, device=dev)
+    for r in range(world):
+        table.first(slots[r], R, want)
+        ok = ok and bool(torch.equal(want, fs[r]))
+        uniq += int((want == torch.arange(r * R, (r + 1) * R, device=dev)).sum().item())
+    return ok, uniq
+
+
+def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e2e, want_cpu, scaling):
+    """One workload on this rank's shard of R records: resident measurement (value, roofline), optional e2e and CPU legs.
+    Returns the JSON line as a dict on rank 0 (None elsewhere)."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     import circkit_b200
     from circkit_b200 import device as D
     from circkit_b200 import exchange as X
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    R = w["records"]
+    w = dict(WORKLOADS[wname])
+    seed = SEEDS[wname]
+    named = R == w["records"] or scaling == "strong"
+    metric = "canonicalize+uniq records/sec" if w["uniq"] else "canonicalize records/sec"
+    config = make_config(args, w, R, named)
     w["mask"] = D.class_mask_for(w["lo"], w["hi"])
-    ctx = circkit_b200.Context(device=local_rank, max_batch_bytes=(256 << 20) if not args.no_e2e else 0,
-                               max_batch_records=(1 << 20) if not args.no_e2e else 0,
-                               table_capacity=R if (w["uniq"] and not args.no_e2e) else 0)
+    e2e_on = want_e2e
+    ctx = circkit_b200.Context(device=local_rank, max_batch_bytes=(256 << 20) if e2e_on else 0,
+                               max_batch_records=(1 << 20) if e2e_on else 0,
+                               table_capacity=R if (w["uniq"] and e2e_on) else 0)
     sampler = ClockSampler(local_rank)                     # started early: nvidia-smi needs ~100 ms to come up
     sampler.start()
     base_index = rank * R
-    raw_dev, subs = None, None
+    raw_dev = None
     if w.get("raw"):
         # config 3: raw record bytes resident in HBM (numpy generator circkit_b200/synth_host.py, 500 k distinct records tiled to
         # the requested count -- generating 5 M on the host would take minutes); every symbol lane is exercised:
         # normalise + classify + pack + canonicalise per step
-        import numpy as np
         from circkit_b200 import synth_host
         tile_n = min(R, 500_000)
         a_np, o_np = synth_host.make_iupac_records(tile_n, w["lo"], w["hi"], seed + rank)
@@ -387,29 +589,11 @@ def main():
         lens_out = torch.empty(R, dtype=torch.int32, device=dev)
         ws = D.Workspace(ctx, R, total_raw, dev)
         w["mask"] = 0
-    elif w["uniq"] and world > 1 and args.chunks > 1:
-        # (experiment, slower than the default) multi-GPU uniq: the rank's shard as `chunks` sub-batches, so that the hash-range exchange of one sub-batch overlaps
-        # the canonicalisation of the next (same records, same order: record g is a pure function of (seed, g))
-        C = max(1, min(args.chunks, R))
-        bounds = [R * c // C for c in range(C + 1)]
-        subs, parts, run = [], [], 0
-        for c in range(C):
-            n_c = bounds[c + 1] - bounds[c]
-            b_c = D.synth_batch(ctx, seed=seed, first_index=base_index + bounds[c], n_records=n_c, kind=w["kind"], lo=w["lo"],
-                                hi=w["hi"], dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
-            subs.append(dict(b=b_c, n=n_c, lo=bounds[c], base=base_index + bounds[c], ws=D.Workspace(ctx, n_c, 0, dev),
-                             outs=D.CanonOutputs(n_c, b_c.total, dev, want_bytes=True, want_hash=True, aligned=True),
-                             part=D.OwnerPartitioner(ctx, n_c, world, dev), ev=torch.cuda.Event()))
-            parts.append(b_c.offsets[:-1] + run)
-            run += b_c.total
-        parts.append(torch.tensor([run], dtype=torch.int64, device=dev))
-        batch = D.DeviceBatch(torch.cat(parts), None, R, run)      # offsets of the whole shard (sizes, e2e)
-        ws = None
     else:
         batch = D.synth_batch(ctx, seed=seed, first_index=base_index, n_records=R, kind=w["kind"], lo=w["lo"], hi=w["hi"],
                               dup_permille=w["dup"], adversarial_permille=w["adv"], device=dev)
         ws = D.Workspace(ctx, R, 0, dev)
-    outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"], aligned=True) if subs is None else None
+    outs = D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=w["uniq"], aligned=True)
     lens = batch.lens
     if w["uniq"]:
         table = D.DeviceTable(ctx, capacity_keys=int(R * 1.05) + 1024, dev=dev)   # owns ~R keys of the global set
@@ -418,11 +602,10 @@ def main():
 
         def first_fn(h, idx):
             m = h.numel()
-            key = m
-            if key not in slot_cache:
-                slot_cache[key] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
-                                   torch.empty(max(m, 1), dtype=torch.int64, device=dev))
-            slots, out = slot_cache[key]
+            if m not in slot_cache:
+                slot_cache[m] = (torch.empty(max(m, 1), dtype=torch.int64, device=dev),
+                                 torch.empty(max(m, 1), dtype=torch.int64, device=dev))
+            slots, out = slot_cache[m]
             table.insert(h, m, slots, index=idx, base_index=base_index if idx is None else 0)
             table.first(slots, m, out)
             return out[:m]
@@ -449,11 +632,25 @@ def main():
             table.first(slots, m, out)
             return out[:m]
 
-    padded = {"on": world > 1 and args.exchange != "exact" and w["uniq"], "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
+    padded = {"on": world > 1 and args.exchange in ("symm", "padded") and w["uniq"], "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
               "peer": None}
-    if padded["on"] and args.exchange == "peer" and subs is None:
-        # peer-mapped buffers need symmetric-memory support on the node; if any rank cannot set them up, every rank takes
-        # the same fixed-capacity buckets through NCCL instead, and the JSON line says so
+    peer_group = None
+    if world > 1 and w["uniq"] and args.exchange == "peer":
+        # the library's own peer group (CUDA IPC).  If any rank cannot set it up, every rank takes the NCCL buckets instead and
+        # the JSON line says so
+        why = ""
+        try:
+            peer_group = D.PeerGroup(ctx, max(R, ctx.max_batch_records, 1), world, rank)
+            ctx._peer_attached = True
+        except Exception as e:                              # noqa: BLE001 -- reported, not hidden
+            why = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+        okt = torch.tensor([1 if peer_group is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if not int(okt.item()):
+            peer_group = None
+            padded["on"] = True
+            config["sharding"] += " [peer group unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
+    if padded["on"] and args.exchange == "symm":
         peer, why = None, ""
         try:
             peer = D.PeerExchange(ctx, R, world, rank, dev)
@@ -464,10 +661,9 @@ def main():
         if int(okt.item()):
             padded["peer"] = peer
         else:
-            config["sharding"] += " [peer memory unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
-    comm = torch.cuda.Stream(device=dev) if subs is not None else None
+            config["sharding"] += " [symmetric memory unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
-    if w["uniq"] and subs is None and raw_dev is None:
+    if w["uniq"] and raw_dev is None:
         overlap = args.overlap
         stage_stream = torch.cuda.Stream(device=dev) if overlap else None
         outs_sets = [outs, D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=True, aligned=True) if overlap else outs]
@@ -476,28 +672,6 @@ def main():
         partitioner = D.OwnerPartitioner(ctx, R, world, dev) if world > 1 else None
 
     def step():
-        if subs is not None:
-            cur = torch.cuda.current_stream()
-            table.clear()
-            comm.wait_stream(cur)                   # the cleared table before any insert
-            pend = []
-
-            def send(sb):
-                with torch.cuda.stream(comm):
-                    comm.wait_event(sb["ev"])
-                    return X.exchange_send(sb["outs"].hash[:sb["n"]], sb["base"], sb["part"], insert_pairs_fn)
-
-            for c, sb in enumerate(subs):
-                D.canon_packed2(ctx, sb["b"], sb["outs"], sb["ws"], class_mask=w["mask"])
-                sb["ev"].record(cur)
-                if c >= 1:
-                    pend.append(send(subs[c - 1]))  # exchange of sub-batch c-1 while sub-batch c is canonicalised
-            pend.append(send(subs[-1]))
-            with torch.cuda.stream(comm):           # every insert of every rank has landed: first index per record
-                for sb, p in zip(subs, pend):
-                    first[sb["lo"]: sb["lo"] + sb["n"]].copy_(X.exchange_finish(p, first_query_fn))
-            cur.wait_stream(comm)
-            return
         if raw_dev is not None:
             D.canon_bytes(ctx, raw_dev, batch.offsets, R, batch.total, outs, lens_out, ws, normalize=True)
             return
@@ -519,6 +693,8 @@ def main():
             table.clear()
             if world == 1:
                 f_i.copy_(first_fn(o_i.hash[:R], None))
+            elif peer_group is not None:            # exact counts, no padding, nothing to check afterwards
+                peer_group.first_index(o_i.hash[:R], base_index, table, f_i)
             elif padded["on"]:
                 # fixed-capacity buckets: no counts to exchange, no host synchronisation in the step; an overflowing bucket is
                 # flagged on the device and checked after the steps have been queued
@@ -537,10 +713,6 @@ def main():
         if stage_stream is not None:
             torch.cuda.current_stream().wait_stream(stage_stream)
 
-    def check_all():
-        for wsp in ([sb["ws"] for sb in subs] if subs is not None else [ws]):
-            D.check(ctx, wsp)
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -548,11 +720,11 @@ def main():
             torch.cuda.synchronize()
 
     t_window0 = time.time()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     drain()
     sync_all()
-    check_all()
+    D.check(ctx, ws)
     if padded["on"]:
         ov = padded["overflow"].clone().to(torch.int64)
         dist.all_reduce(ov, op=dist.ReduceOp.MAX)
@@ -560,7 +732,8 @@ def main():
             padded["on"] = False
             padded["peer"] = None
             padded["overflow"].zero_()
-            for _ in range(args.warmup):
+            config["sharding"] += " [a fixed-capacity bucket overflowed in the warm-up: exact-count exchange instead]"
+            for _ in range(warmup):
                 step()
             drain()
             sync_all()
@@ -570,7 +743,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     drain()
     e1.record()
@@ -580,16 +753,19 @@ def main():
         raise RuntimeError("padded exchange overflowed inside the timed steps although the warm-up steps on the same data did not")
     if pipe is not None:
         first = first_sets[(pipe["k"] - 1) & 1]             # result of the last step
+        outs_last = outs_sets[(pipe["k"] - 1) & 1]
+    else:
+        outs_last = outs
     clocks = sampler.stop(t_window0, time.time())
     launches = ctx.launch_count() - launches0
     ktimes = D.kernel_times(ctx)
     ctx._lib.ck_kernel_timing(ctx.handle, 0)
-    check_all()
+    D.check(ctx, ws)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     total_records = R * world
     total_bases = batch.total
     if world > 1:
@@ -597,6 +773,18 @@ def main():
         dist.all_reduce(tb)
         total_bases = int(tb.item())
     value = total_records / (ms_per_step / 1e3)
+
+    # ---------------- multi-rank parity: the global first-occurrence index, rebuilt on rank 0 with the single-GPU table
+    global_parity, global_unique = None, None
+    if w["uniq"]:
+        if world > 1:
+            global_parity, global_unique = global_first_index_check(ctx, D, torch, dist, dev, rank, world, R, outs_last.hash, first)
+            flag = torch.tensor([1 if (rank != 0 or global_parity) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()):
+                raise RuntimeError("multi-rank uniq: first indices of the exchange differ from the single-table rebuild on rank 0")
+        else:
+            global_unique = int((first == torch.arange(base_index, base_index + R, device=dev)).sum().item())
 
     # ---------------- roofline of the dominant kernel (rank 0's launches)
     from circkit_b200.device import CLASS_NAMES
@@ -619,135 +807,38 @@ def main():
         alg_bytes = int((2 * sel + 16).sum().item())
     else:
         alg_bytes = int((8 * ((sel + 31) // 32) + sel + 16 + (8 if w["uniq"] else 0)).sum().item())
-    launches_per_step = max(ktimes[dom][1], 1) / args.steps          # > 1 when the shard runs as sub-batches
-    dom_ms = ktimes[dom][0] / args.steps                              # per step: all launches of the dominant kernel
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    launches_per_step = max(ktimes[dom][1], 1) / steps
+    dom_ms = ktimes[dom][0] / steps                                   # per step: all launches of the dominant kernel
+    peak, peak_src = _peak()
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            tj = json.load(open(tpath))
+            traffic = tj.get(wname, {}).get(dom)
             if traffic is not None:
                 traffic = int(traffic / launches_per_step)
+                traffic_src = "ncu --set full, separate run (%s)" % tj.get("_source", "profiles/")
         except Exception:
             traffic = None
-    kernel_share = {c: round(ktimes[c][0] / args.steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
-    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s2 (lane per record, streaming)", dom),
+    kernel_share = {c: round(ktimes[c][0] / steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s3 (lane per record, streaming, 256-bit loads)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes / launches_per_step),
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes / launches_per_step),
                 "kernel_ms_per_launch": dom_ms / launches_per_step, "launches_per_step": launches_per_step,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,
                 "step_ms": ms_per_step}
 
     # ---------------- e2e through the host-buffer C ABI (pinned host memory, copies timed)
     e2e = None
-    if not args.no_e2e:
-        import ctypes as C
-        import numpy as np
-        if raw_dev is not None:
-            ascii_dev = raw_dev
-        elif subs is not None:
-            ascii_dev = torch.cat([D.unpack_ascii(ctx, sb["b"]) for sb in subs])
-        else:
-            ascii_dev = D.unpack_ascii(ctx, batch)
-        off_host = batch.offsets.cpu().numpy().astype(np.uint64)
-        # multi-rank runs: every rank pins its own copy of the input; bound it to 4 GiB of record bytes per rank (the first
-        # R_e records of the shard -- the same steady-state batches, fewer of them)
-        R_e = R
-        if world > 1 and int(off_host[R]) > (4 << 30):
-            R_e = max(1, int(np.searchsorted(off_host, 4 << 30, side="right")) - 1)
-        total = int(off_host[R_e])
-        lib = ctx._lib
-        h_bytes_p = lib.ck_alloc_pinned(ctx.handle, total + 64)
-        h_bytes = np.ctypeslib.as_array(C.cast(h_bytes_p, C.POINTER(C.c_uint8)), shape=(total + 64,))
-        pinned_view = torch.from_numpy(h_bytes)
-        pinned_view[:total].copy_(ascii_dev[:total])
-        del ascii_dev
-        # batches of <= 256 MiB / <= 1 Mi records, alternating the two slots
-        max_b, max_r = 256 << 20, 1 << 20
-        cuts = [0]
-        while cuts[-1] < R_e:
-            lo_i = cuts[-1]
-            hi_i = min(R_e, lo_i + max_r)
-            limit = int(off_host[lo_i]) + max_b
-            if int(off_host[hi_i]) > limit:
-                hi_i = int(np.searchsorted(off_host, limit, side="right")) - 1
-            cuts.append(max(hi_i, lo_i + 1))
-        nb = len(cuts) - 1
-        rel_offs, pins = [], []
-        for b in range(nb):
-            ro = (off_host[cuts[b]: cuts[b + 1] + 1] - off_host[cuts[b]]).copy()
-            p = lib.ck_alloc_pinned(ctx.handle, ro.nbytes)
-            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(len(ro),))
-            arr[:] = ro
-            rel_offs.append(arr); pins.append(p)
-        out_first_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R_e + 1))
-        out_hash_p = lib.ck_alloc_pinned(ctx.handle, 8 * (R_e + 1))
-        out_len_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R_e + 1))
-        out_start_p = lib.ck_alloc_pinned(ctx.handle, 4 * (R_e + 1))
-        out_strand_p = lib.ck_alloc_pinned(ctx.handle, (R_e + 1))
-        # CK_F_NO_BYTES: `circkit uniq` without -c echoes the input bytes; result = first_index per record (config 3:
-        # + CK_F_NORMALIZE, the CLI path)
-        flags = 2 | (1 if raw_dev is not None else 0)
-
-        def e2e_step():
-            if w["uniq"]:
-                ctx.uniq_reset()
-            for b in range(nb + 1):
-                if b < nb:
-                    bp = h_bytes_p + int(off_host[cuts[b]])
-                    nrec = cuts[b + 1] - cuts[b]
-                    if w["uniq"]:
-                        rc = lib.ck_uniq_submit(ctx.handle, b & 1, bp, rel_offs[b].ctypes.data, nrec, flags, base_index + cuts[b])
-                    else:
-                        rc = lib.ck_canon_submit(ctx.handle, b & 1, bp, rel_offs[b].ctypes.data, nrec, flags)
-                    ctx._check(rc)
-                if b >= 1:
-                    pb = b - 1
-                    c0 = cuts[pb]
-                    if w["uniq"]:
-                        rc = lib.ck_uniq_wait(ctx.handle, pb & 1, None, out_len_p + 4 * c0, out_hash_p + 8 * c0, out_first_p + 8 * c0)
-                    else:
-                        rc = lib.ck_canon_wait(ctx.handle, pb & 1, None, out_len_p + 4 * c0, out_start_p + 4 * c0,
-                                               out_strand_p + c0, None)
-                    ctx._check(rc)
-
-        e2e_step()                         # warm-up
-        sync_all()
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        h2d = total + 8 * (R_e + nb)
-        d2h = (R_e * (8 + 8 + 4)) if w["uniq"] else (R_e * (4 + 4 + 1))
-        # parity spot check of the e2e result against the device-resident result (multi-rank: local keys only)
-        if w["uniq"] and world == 1:
-            got = np.ctypeslib.as_array(C.cast(out_first_p, C.POINTER(C.c_uint64)), shape=(R_e,))
-            assert np.array_equal(got, first.cpu().numpy().astype(np.uint64)), "e2e first_index != resident first_index"
-        e2e = {"value": R_e * world / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "batches_per_step": nb,
-               "api": "ck_uniq_submit/ck_uniq_wait" if w["uniq"] else "ck_canon_submit/ck_canon_wait",
-               "input": "ASCII record bytes + offsets in pinned host memory (normalise+pack on device)",
-               "result": "first_index + hash64 + length per record" if w["uniq"] else "start + strand + length per record",
-               "gbases_per_s": total * world / (dt / e2e_steps) / 1e9, "records_per_gpu_per_step": R_e,
-               "note": "multi-rank e2e dedups per rank (no exchange); the resident path does the global exchange" if world > 1 else ""}
-        for p in pins + [out_first_p, out_hash_p, out_len_p, out_start_p, out_strand_p, h_bytes_p]:
-            lib.ck_free_pinned(ctx.handle, p)
+    if want_e2e:
+        e2e = e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, first if w["uniq"] else None, sync_all, steps)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and want_cpu:
         r = cpu_arm(w, seed, args.cpu_seconds, 3, 1, w["uniq"])
         cpu = {"value": r["records_per_s"], "unit": "records/s", "cores": r["cores"], "kind": "port",
                "gbases_per_s": r["gbases_per_s"],
@@ -756,19 +847,91 @@ def main():
                          "(conservative)" % (r["sample_records"], r["sample_bases"] / 1e6, r["cores"]),
                "faithful_cost_footnote": cpu_faithful_footnote(w, seed)}
 
+    line = None
     if rank == 0:
-        survivors = int((first == torch.arange(base_index, base_index + R, device=dev)).sum().item()) if w["uniq"] else None
-        line = {"metric": metric, "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": metric, "value": value, "unit": "records/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "gbases_per_s": total_bases / (ms_per_step / 1e3) / 1e9, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "rank0_unique_records": survivors}
+                "global_unique_records": global_unique, "global_parity": global_parity,
+                "global_parity_how": ("every rank's hash64 + first_index gathered on rank 0; first index rebuilt over all %d keys "
+                                      "with the single-GPU table and compared" % total_records) if world > 1 and w["uniq"] else None}
+    ctx.close()
+    del batch, outs, ws
+    if w["uniq"]:
+        del table, first, outs_sets, first_sets
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "mono":
+        if rank == 0:
+            (bench_monomerize_reference if args.impl == "reference" else bench_monomerize)(args)
+        return
+
+    # ---------------- reference arm: the CPU path, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = dict(WORKLOADS[args.workload])
+        seed = SEEDS[args.workload]
+        if args.records:
+            w["records"] = args.records
+        metric = "canonicalize+uniq records/sec" if w["uniq"] else "canonicalize records/sec"
+        r = cpu_arm(w, seed, max(args.cpu_seconds, 4.0 * (args.steps + args.warmup)), args.steps, args.warmup, w["uniq"])
+        sample = ("oracle port of circKit's path (Duval x2 + revcomp + compare, xxh3, keep-first map; O(1) byte "
+                  "indexing -- conservative: the reference's chars().nth(i) is O(i)); a bounded SAMPLE of %d records / %.1f Mbases of the "
+                  "workload per step (a rate, not the %d records of the named config), worker stage on %d threads, consumer stage "
+                  "serial, step = max of the two" % (r["sample_records"], r["sample_bases"] / 1e6, w["records"], r["cores"]))
+        config = make_config(args, w, w["records"], not args.records)
+        line = {"impl": "reference", "metric": metric, "value": r["records_per_s"], "unit": "records/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config, "gbases_per_s": r["gbases_per_s"],
+                "cpu_baseline": {"value": r["records_per_s"], "unit": "records/s", "cores": r["cores"], "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": r["records_per_s"], "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "reference_sample": {"records_per_step": r["sample_records"], "bases_per_step": r["sample_bases"],
+                                     "note": "each step is a bounded sample of the workload: the value is a rate"},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R = args.records or WORKLOADS[args.workload]["records"]
+    line = b200_arm(args, args.workload, R, rank, local_rank, world, dev, args.steps, args.warmup,
+                    want_e2e=not args.no_e2e, want_cpu=not args.no_cpu, scaling="weak")
+    # ---------------- config 5 as the north star states it: ONE 100 M-record uniq split over the N GPUs (strong scaling),
+    # reported as a sub-record of the same line
+    if args.workload == "c2" and not args.no_config5 and not args.records:
+        total5 = args.c5_records
+        R5 = total5 // world
+        sub = b200_arm(args, "c5", R5, rank, local_rank, world, dev, max(2, min(args.steps, 5)), 3,
+                       want_e2e=False, want_cpu=False, scaling="strong")
+        if rank == 0:
+            line["config5"] = {k: sub[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling",
+                                                    "gbases_per_s", "gpu_launches", "global_unique_records", "global_parity")}
+            line["config5"]["records_total"] = R5 * world
+            line["config5"]["records_per_gpu"] = R5
+            line["config5"]["workload"] = "config 5: uniq over %d viroid-length records (250-400 nt, 30%% duplicates), split over %d GPU(s)" % (R5 * world, world)
+            line["config5"]["roofline"] = {k: sub["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "kernel_ms_per_launch", "class_kernel_ms_per_step")}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -73,6 +74,11 @@ u32 cls_smem_bytes(int c)
 // One set of tie-path scratch buffers: kernels of one in-flight batch use one set.
 struct ExecScratch {
     u32 *tie[CLS_COUNT] = {};
+    // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
+    // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing.  One set
+    // per in-flight batch (slot 0, slot 1, the device-resident API), so batches never queue behind each other's forks.
+    cudaStream_t side_stream[CLS_COUNT] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[CLS_COUNT] = {};
 };
 
 struct Slot {
@@ -115,13 +121,16 @@ struct ck_ctx {
     bool have_last_insert = false;
     TableSlot *table = nullptr; u64 table_slots = 0; u64 *side = nullptr; u32 *d_overflow = nullptr;
     PeerGroup peer;                     // world > 1 after ck_peer_attach: uniq runs the hash-range exchange
+    // library drop-ins (ck_lmsr_index / ck_lmsr / ck_canonicalize): persistent staging + stream, one call at a time per
+    // context (any number of host threads may call; lib/src/canonicalize.rs:54 is called from T worker threads)
+    std::mutex lib_mu;
+    cudaStream_t lib_stream = nullptr;
+    u8 *lib_h = nullptr, *lib_d = nullptr; size_t lib_h_bytes = 0, lib_d_bytes = 0;
+    ExecScratch lib_scr;
     u64 launches = 0;
     bool attrs_set = false;
+    u32 s3_debug = 0;                   // CK_S3_DEBUG: bits 8.. switch the lane kernel's L2 prefetches off (traffic experiments)
     int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
-    // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
-    // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing
-    cudaStream_t side_stream[CLS_COUNT] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[CLS_COUNT] = {};
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
     std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 3];     // [CLS_COUNT] = lane kernel, then table insert, table first
@@ -180,6 +189,11 @@ void fill_tables(Tables &t, u8 secret[200])
 
 int alloc_scratch(ck_ctx *ctx, ExecScratch &s)
 {
+    CK_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    for (int c = 0; c < CLS_COUNT; c++) {
+        CK_CUDA(ctx, cudaStreamCreateWithFlags(&s.side_stream[c], cudaStreamNonBlocking));
+        CK_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_join[c], cudaEventDisableTiming));
+    }
     for (int c = 0; c < CLS_COUNT; c++) {
         if (kCls[c].bits == 0) continue;
         const u64 groups = (u64)kCls[c].ctas_per_sm * ctx->num_sms * (kCls[c].cta ? 1u : kCls[c].threads / 32u);
@@ -189,7 +203,14 @@ int alloc_scratch(ck_ctx *ctx, ExecScratch &s)
 }
 void free_scratch(ExecScratch &s)
 {
-    for (int c = 0; c < CLS_COUNT; c++) { if (s.tie[c]) cudaFree(s.tie[c]); s.tie[c] = nullptr; }
+    for (int c = 0; c < CLS_COUNT; c++) {
+        if (s.tie[c]) cudaFree(s.tie[c]);
+        if (s.side_stream[c]) cudaStreamDestroy(s.side_stream[c]);
+        if (s.ev_join[c]) cudaEventDestroy(s.ev_join[c]);
+        s.tie[c] = nullptr; s.side_stream[c] = nullptr; s.ev_join[c] = nullptr;
+    }
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    s.ev_fork = nullptr;
 }
 
 template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
@@ -322,6 +343,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
         else { a.list = sorted; a.count = io.counts + 12; a.n_direct = 0; a.min_n = 1; a.max_n = cls_max_n(CLS_W2X); }
         const int v = (a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0) | (a.list ? CK_W2_LIST : 0);
+        a.mode |= ctx->s3_debug;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, true, st));
         s2_launch(ctx, st, a, v);
@@ -331,8 +353,8 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     u32 to_launch = 0;
     for (int c = 0; c < CLS_COUNT; c++)
         if (c != CLS_HUGE && !(class_mask && !(class_mask & (1u << c)))) to_launch++;
-    const bool fork = ctx->ev_fork != nullptr && to_launch >= 2;
-    if (fork) CK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    const bool fork = scr.ev_fork != nullptr && to_launch >= 2;
+    if (fork) CK_CUDA(ctx, cudaEventRecord(scr.ev_fork, st));
     u32 joined = 0;
     for (int c = 0; c < CLS_COUNT; c++) {
         if (c == CLS_HUGE) continue;
@@ -348,8 +370,8 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         // CTA-per-record kernels fill the GPU by themselves and keep their place on the caller's stream; the warp-per-record
         // launches (retry lists, byte lanes, empty records) are the small ones that gain from running side by side
         const bool side = fork && !kCls[c].cta;
-        cudaStream_t sc = side ? ctx->side_stream[c] : st;
-        if (side) CK_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        cudaStream_t sc = side ? scr.side_stream[c] : st;
+        if (side) CK_CUDA(ctx, cudaStreamWaitEvent(sc, scr.ev_fork, 0));
         CK_CUDA(ctx, timed(c, e0, e1, true, sc));
         switch (c) {
         case CLS_W2S: k_canon_w2<true, -1><<<grid, thr, smem, sc>>>(a); break;
@@ -362,11 +384,11 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         case CLS_EMPTY: k_canon_empty<<<(u32)ctx->num_sms, 256, 0, sc>>>(a); break;
         }
         CK_CUDA(ctx, timed(c, e0, e1, false, sc));
-        if (side) { CK_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc)); joined |= 1u << c; }
+        if (side) { CK_CUDA(ctx, cudaEventRecord(scr.ev_join[c], sc)); joined |= 1u << c; }
         ctx->launches++;
     }
     for (int c = 0; c < CLS_COUNT; c++)
-        if ((joined >> c) & 1u) CK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+        if ((joined >> c) & 1u) CK_CUDA(ctx, cudaStreamWaitEvent(st, scr.ev_join[c], 0));
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }
@@ -623,6 +645,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     if (!ctx) return fail(nullptr, CK_ERR_ARG, "out of host memory");
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
+    if (const char *dbg = getenv("CK_S3_DEBUG")) ctx->s3_debug = (u32)strtoul(dbg, nullptr, 0) & 0xff00u;
     if (const char *lk = getenv("CK_LANE_KERNEL")) ctx->lane_kernel = atoi(lk) == 2 ? 2 : 3;
 #define CK_INIT(call)                                                                          \
     do {                                                                                       \
@@ -646,12 +669,9 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
         CK_INIT(cudaMemcpyToSymbol(c_mergesec, merge, sizeof(merge)));
         CK_INIT(cudaMemcpyToSymbol(c_midsec, mid, sizeof(mid)));
     }
-    CK_INIT(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    for (int c = 0; c < CLS_COUNT; c++) {
-        CK_INIT(cudaStreamCreateWithFlags(&ctx->side_stream[c], cudaStreamNonBlocking));
-        CK_INIT(cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming));
-    }
     if (alloc_scratch(ctx, ctx->dev_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
+    if (alloc_scratch(ctx, ctx->lib_scr)) { g_init_error = ctx->err; ck_destroy(ctx); return CK_ERR_CUDA; }
+    CK_INIT(cudaStreamCreateWithFlags(&ctx->lib_stream, cudaStreamNonBlocking));
     const u64 B = cfg->max_batch_bytes, R = cfg->max_batch_records;
     if (B || R) {
         for (int k = 0; k < 2; k++) {
@@ -710,17 +730,16 @@ void ck_destroy(ck_ctx *ctx)
         free_scratch(s.scr);
     }
     free_scratch(ctx->dev_scr);
+    free_scratch(ctx->lib_scr);
+    if (ctx->lib_stream) cudaStreamDestroy(ctx->lib_stream);
+    if (ctx->lib_h) cudaFreeHost(ctx->lib_h);
+    if (ctx->lib_d) cudaFree(ctx->lib_d);
     {
         PeerGroup &P = ctx->peer;
         for (u32 r = 0; r < P.world && P.attached; r++) if (r != P.rank && P.mapped[r]) cudaIpcCloseMemHandle(P.mapped[r]);
         for (int k = 0; k < 2; k++) { if (P.pos[k]) cudaFree(P.pos[k]); if (P.cursors[k]) cudaFree(P.cursors[k]); if (P.slot_of[k]) cudaFree(P.slot_of[k]); }
         if (P.block) cudaFree(P.block);
     }
-    for (int c = 0; c < CLS_COUNT; c++) {
-        if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
-        if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
-    }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->table) cudaFree(ctx->table);
     if (ctx->side) cudaFree(ctx->side);
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
@@ -828,48 +847,106 @@ int ck_uniq_reset(ck_ctx *ctx)
 }
 
 // ---- single-record / library-semantics entry points -------------------------------------------
+// Small batches (the single-record calls above all): ONE launch of the generic CTA-per-record kernel on the raw bytes (the
+// byte lane is library semantics by construction: bytes as they are, bio's 256-entry complement table), one copy in and
+// one copy out through persistent pinned staging on the context's own stream -- no allocation, no default-stream round
+// trip.  Larger batches take the full pipeline (k_prepare + lanes) with a workspace that is kept and grown on demand.
+static int lib_reserve(ck_ctx *ctx, size_t h_bytes, size_t d_bytes)
+{
+    if (h_bytes > ctx->lib_h_bytes) {
+        if (ctx->lib_h) cudaFreeHost(ctx->lib_h);
+        ctx->lib_h = nullptr; ctx->lib_h_bytes = 0;
+        const size_t want = std::max<size_t>(h_bytes * 2, 1 << 16);
+        CK_CUDA(ctx, cudaMallocHost(&ctx->lib_h, want));
+        ctx->lib_h_bytes = want;
+    }
+    if (d_bytes > ctx->lib_d_bytes) {
+        if (ctx->lib_d) cudaFree(ctx->lib_d);
+        ctx->lib_d = nullptr; ctx->lib_d_bytes = 0;
+        const size_t want = std::max<size_t>(d_bytes * 2, 1 << 16);
+        CK_CUDA(ctx, cudaMalloc(&ctx->lib_d, want));
+        ctx->lib_d_bytes = want;
+    }
+    return CK_OK;
+}
 static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint32_t n_records, u32 mode,
                      uint8_t *out_bytes, uint32_t *out_start, uint8_t *out_strand)
 {
     if (!ctx || !offsets) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     if (n_records == 0) return CK_OK;
-    const u64 total = offsets[n_records];
+    const u64 total = offsets[n_records] - offsets[0];
+    if (offsets[0] != 0) return fail(ctx, CK_ERR_ARG, "offsets[0] must be 0");
+    if (total && !bytes) return fail(ctx, CK_ERR_ARG, "null argument");
+    u64 longest = 0;
+    for (u32 i = 0; i < n_records; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, CK_ERR_ARG, "offsets must be non-decreasing");
+        longest = std::max<u64>(longest, offsets[i + 1] - offsets[i]);
+    }
+    if (longest > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+    std::lock_guard<std::mutex> lock(ctx->lib_mu);
     CK_CUDA(ctx, cudaSetDevice(ctx->device));
-    u8 *d_raw = nullptr, *d_norm = nullptr, *d_out = nullptr, *d_lane = nullptr, *d_strand = nullptr;
-    u64 *d_off = nullptr, *d_p2 = nullptr; u32 *d_len = nullptr, *d_start = nullptr, *d_lists = nullptr, *d_counts = nullptr;
-    const size_t R = n_records;
-    int rc = CK_OK;
-    u32 h_counts[16] = {};
-    cudaError_t e = cudaSuccess;
-#define CK_LB(call) do { if (e == cudaSuccess) e = (call); } while (0)
-    CK_LB(cudaMalloc(&d_raw, total + 16)); CK_LB(cudaMalloc(&d_norm, total + 16)); CK_LB(cudaMalloc(&d_out, total + 16));
-    CK_LB(cudaMalloc(&d_p2, p2_words(total, R) * 8)); CK_LB(cudaMalloc(&d_off, (R + 1) * 8));
-    CK_LB(cudaMalloc(&d_len, R * 4)); CK_LB(cudaMalloc(&d_lane, R)); CK_LB(cudaMalloc(&d_start, R * 4));
-    CK_LB(cudaMalloc(&d_strand, R)); CK_LB(cudaMalloc(&d_lists, lists_bytes_for(R))); CK_LB(cudaMalloc(&d_counts, 256));
-    CK_LB(cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice));
-    if (total) CK_LB(cudaMemcpy(d_raw, bytes, total, cudaMemcpyHostToDevice));
-    if (e == cudaSuccess) {
-        PrepareArgs pa{d_raw, d_off, n_records, 0u, d_p2, d_norm, d_len, d_lane};
-        k_prepare<<<ctx->num_sms * 32, 256>>>(pa);
-        k_extend_packed2<<<extend_grid(ctx, n_records), 256>>>(d_p2, d_off, d_len, d_lane, n_records, nullptr);
-        ctx->launches += 2;
-        CanonIO io{};
-        io.packed2 = d_p2; io.bytes = d_norm; io.offsets = d_off; io.lens = d_len; io.lane = d_lane; io.n = n_records;
-        io.mode = mode; io.out = out_bytes ? d_out : nullptr; io.out_start = d_start; io.out_strand = d_strand;
-        io.out_hash = nullptr; io.lists = d_lists; io.lists_bytes = lists_bytes_for(R); io.counts = d_counts;
-        rc = run_canon(ctx, 0, ctx->dev_scr, io, 0);
-    }
-    if (rc == CK_OK) {
-        CK_LB(cudaMemcpy(h_counts, d_counts, 64, cudaMemcpyDeviceToHost));
-        if (out_bytes && total) CK_LB(cudaMemcpy(out_bytes, d_out, total, cudaMemcpyDeviceToHost));
-        if (out_start) CK_LB(cudaMemcpy(out_start, d_start, R * 4, cudaMemcpyDeviceToHost));
-        if (out_strand) CK_LB(cudaMemcpy(out_strand, d_strand, R, cudaMemcpyDeviceToHost));
-    }
-#undef CK_LB
-    void *ptrs[] = {d_raw, d_norm, d_out, d_p2, d_off, d_len, d_lane, d_start, d_strand, d_lists, d_counts};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    int rc = set_attrs(ctx);
     if (rc) return rc;
-    if (e != cudaSuccess) return fail(ctx, CK_ERR_CUDA, "library-semantics batch", e);
+    cudaStream_t st = ctx->lib_stream;
+    const size_t R = n_records;
+    const size_t off_bytes = (R + 1) * 8, in_bytes = off_bytes + ((total + 15) & ~15ull);
+    const size_t res_bytes = R * 4 + ((R + 15) & ~15ull) + total;             // start | strand | canonical bytes
+    const bool small = n_records <= 256 && longest <= cls_max_n(CLS_C8);
+    if (small) {
+        if ((rc = lib_reserve(ctx, in_bytes + res_bytes + 64, in_bytes + res_bytes + 64))) return rc;
+        u8 *h_in = ctx->lib_h, *h_res = ctx->lib_h + in_bytes;
+        u8 *d_in = ctx->lib_d, *d_res = ctx->lib_d + in_bytes;
+        memcpy(h_in, offsets, off_bytes);
+        if (total) memcpy(h_in + off_bytes, bytes, total);
+        CK_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, off_bytes + total, cudaMemcpyHostToDevice, st));
+        CanonArgs a{};
+        a.bytes = d_in + off_bytes; a.offsets = reinterpret_cast<const u64 *>(d_in); a.n_direct = n_records;
+        a.out_start = reinterpret_cast<u32 *>(d_res); a.out_strand = d_res + R * 4;
+        a.out = out_bytes ? d_res + R * 4 + ((R + 15) & ~15ull) : nullptr;
+        a.scratch = ctx->lib_scr.tie[CLS_C8]; a.scratch_stride = cls_tie_words(CLS_C8); a.smem_units = cls_units(CLS_C8);
+        a.mode = mode; a.min_n = 1; a.max_n = cls_max_n(CLS_C8);
+        const u32 grid = std::min<u32>(n_records, kCls[CLS_C8].ctas_per_sm * (u32)ctx->num_sms);
+        k_canon_cta<8, false><<<grid, kCls[CLS_C8].threads, cls_smem_bytes(CLS_C8), st>>>(a);
+        ctx->launches++;
+        if (longest != offsets[n_records] / std::max<u32>(n_records, 1) || total == 0 || n_records > 1) {   // any empty record?
+            bool any_empty = false;
+            for (u32 i = 0; i < n_records && !any_empty; i++) any_empty = offsets[i + 1] == offsets[i];
+            if (any_empty) { k_canon_empty<<<1, 256, 0, st>>>(a); ctx->launches++; }
+        }
+        CK_CUDA(ctx, cudaGetLastError());
+        CK_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, out_bytes ? res_bytes : R * 4 + R, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (out_start) memcpy(out_start, h_res, R * 4);
+        if (out_strand) memcpy(out_strand, h_res + R * 4, R);
+        if (out_bytes && total) memcpy(out_bytes, h_res + R * 4 + ((R + 15) & ~15ull), total);
+        return CK_OK;
+    }
+    // the full pipeline; workspace: raw | norm | out | p2 | off | len | lane | start | strand | lists | counts
+    size_t o = 0;
+    auto take = [&](size_t bytes_) { const size_t at = o; o += (bytes_ + 255) & ~(size_t)255; return at; };
+    const size_t o_raw = take(total + 16), o_norm = take(total + 16), o_out = take(total + 16), o_p2 = take(p2_words(total, R) * 8);
+    const size_t o_off = take((R + 1) * 8), o_len = take(R * 4), o_lane = take(R), o_start = take(R * 4), o_strand = take(R);
+    const size_t o_lists = take(lists_bytes_for(R)), o_counts = take(256);
+    if ((rc = lib_reserve(ctx, 64, o))) return rc;
+    u8 *d = ctx->lib_d;
+    u32 h_counts[16] = {};
+    CK_CUDA(ctx, cudaMemcpyAsync(d + o_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) CK_CUDA(ctx, cudaMemcpyAsync(d + o_raw, bytes, total, cudaMemcpyHostToDevice, st));
+    PrepareArgs pa{d + o_raw, (u64 *)(d + o_off), n_records, 0u, (u64 *)(d + o_p2), d + o_norm, (u32 *)(d + o_len), d + o_lane};
+    k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>((u64 *)(d + o_p2), (u64 *)(d + o_off), (u32 *)(d + o_len), d + o_lane, n_records, nullptr);
+    ctx->launches += 2;
+    CanonIO io{};
+    io.packed2 = (u64 *)(d + o_p2); io.bytes = d + o_norm; io.offsets = (u64 *)(d + o_off); io.lens = (u32 *)(d + o_len); io.lane = d + o_lane;
+    io.n = n_records; io.mode = mode; io.out = out_bytes ? d + o_out : nullptr; io.out_start = (u32 *)(d + o_start); io.out_strand = d + o_strand;
+    io.out_hash = nullptr; io.lists = (u32 *)(d + o_lists); io.lists_bytes = lists_bytes_for(R); io.counts = (u32 *)(d + o_counts);
+    rc = run_canon(ctx, st, ctx->lib_scr, io, 0);
+    if (rc) return rc;
+    CK_CUDA(ctx, cudaMemcpyAsync(h_counts, d + o_counts, 64, cudaMemcpyDeviceToHost, st));
+    if (out_bytes && total) CK_CUDA(ctx, cudaMemcpyAsync(out_bytes, d + o_out, total, cudaMemcpyDeviceToHost, st));
+    if (out_start) CK_CUDA(ctx, cudaMemcpyAsync(out_start, d + o_start, R * 4, cudaMemcpyDeviceToHost, st));
+    if (out_strand) CK_CUDA(ctx, cudaMemcpyAsync(out_strand, d + o_strand, R, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
     if (h_counts[CLS_HUGE]) return fail(ctx, CK_ERR_TOO_LONG, "record beyond the staged-length classes");
     return CK_OK;
 }
@@ -929,10 +1006,19 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
                        uint64_t workspace_bytes)
 {
     if (!ctx) return CK_ERR_ARG;
-    if (!out_len) return fail(ctx, CK_ERR_ARG, "out_len is required");
-    if (!total_bytes || workspace_bytes < ck_dev_workspace_bytes(n_records, total_bytes))
-        return fail(ctx, CK_ERR_ARG, "workspace too small");
     if (!n_records) return CK_OK;
+    if (!out_len) return fail(ctx, CK_ERR_ARG, "out_len is required");
+    if (workspace_bytes < ck_dev_workspace_bytes(n_records, total_bytes)) return fail(ctx, CK_ERR_ARG, "workspace too small");
+    if (!total_bytes) {
+        // a batch of empty records only is valid (the host path accepts it too): every record goes to the empty class
+        cudaStream_t st0 = (cudaStream_t)stream;
+        CK_CUDA(ctx, cudaMemsetAsync(out_len, 0, (size_t)n_records * 4, st0));
+        CanonIO io0{};
+        io0.offsets = U(offsets); io0.lens = out_len; io0.n = n_records; io0.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
+        io0.out_start = out_start; io0.out_strand = out_strand; io0.out_hash = U(out_hash64);
+        io0.counts = (u32 *)workspace; io0.lists = (u32 *)((u8 *)workspace + 256); io0.lists_bytes = lists_bytes_for(n_records);
+        return run_canon(ctx, st0, ctx->dev_scr, io0, class_mask);
+    }
     u8 *w = (u8 *)workspace;
     u32 *counts = (u32 *)w; w += 256;
     u32 *lists = (u32 *)w; w += lists_bytes_for(n_records);

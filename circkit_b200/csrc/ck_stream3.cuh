@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
     const u32 count = use_list ? *a.count : a.n_direct;
     if (use_list) a.list += a.count[16];
     const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
+    const bool pf_scan = !(a.mode & 0x100u), pf_head = !(a.mode & 0x400u);   // CK_S3_DEBUG: L2 prefetches off
     // request the head of a record (octs 0 and 1, the units of its last scan step) into this lane's head slot, one batch
     // ahead, and the rest of a short record into L2
     auto fetch_head = [&](u64 off1, u32 n1, u32 rec1) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
         const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
         cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32); cp_async16(head + 48, nb + 48);
         cp_async8(head + 64, nb + 8 * s1); cp_async8(head + 72, nb + 8 * s1 + 8);
-        if (n1 <= 1024u) {                                         // short records (short batches): both copies -> L2
+        if (n1 <= 1024u && pf_head) {                              // short records (short batches): both copies -> L2
             const u32 span = (n1 >> 1) + 48u;
             if (span > 64u) prefetch_l2(nb + 64);
             if (span > 128u) prefetch_l2(nb + 128);
@@ -163,10 +164,12 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
             OA.lo = H0; OA.hi = H1; OB.lo = H2; OB.hi = H3;
             u32 r0 = w2_revcomp(OA.lo.x);
             const u32 iters = (S1max + 3) >> 2;
-#ifdef CK_S3_SCAN_MOV
+#ifndef CK_S3_AHEAD
+#ifndef CK_S3_SCAN_UNROLL
 #define CK_S3_AHEAD 3u
 #else
 #define CK_S3_AHEAD 2u
+#endif
 #endif
 #define CK_S3_STEP(t, x0, x1, x2, q0, q1, q2)                                                                          \
             {                                                                                                          \
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
 #define CK_S3_SCAN(O, O1, O2)                                                                                          \
             {                                                                                                          \
                 O2 = ldg256_here(base + 32 * min(j + CK_S3_AHEAD, omax));                                              \
-                if ((j & 1u) == 0) prefetch_l2(base + 32 * min(j + 8, omax));                                          \
+                if ((j & 1u) == 0 && pf_scan) prefetch_l2(base + 32 * min(j + 8, omax));                                          \
                 const u32 r1 = w2_revcomp(O.lo.y), r2 = w2_revcomp(O.lo.z), r3 = w2_revcomp(O.lo.w);                   \
                 const u32 r4 = w2_revcomp(O.hi.x), r5 = w2_revcomp(O.hi.y), r6 = w2_revcomp(O.hi.z);                   \
                 const u32 r7 = w2_revcomp(O.hi.w), r8 = w2_revcomp(O1.lo.x);                                           \
@@ -192,14 +195,21 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
             }
             if (iters) {
                 u32 j = 0;
-#ifdef CK_S3_SCAN_MOV
+#ifndef CK_S3_SCAN_UNROLL
                 // one loop body, the three octs rotate by register moves (OB has been used, OC was requested an iteration ago)
                 OC = ldg256_here(base + 32 * min(2u, omax));
+#if CK_S3_AHEAD == 4
+                Oct OD = ldg256_here(base + 32 * min(3u, omax));
+#endif
 #pragma unroll 1
                 for (;;) {
                     Oct ON;
                     CK_S3_SCAN(OA, OB, ON)
+#if CK_S3_AHEAD == 4
+                    OA = OB; OB = OC; OC = OD; OD = ON;
+#else
                     OA = OB; OB = OC; OC = ON;
+#endif
                 }
 #else
 #pragma unroll 1
@@ -291,6 +301,14 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
             const u32 o0 = fast ? (Bv >> 7) << 5 : 0u;
             int onext = fast ? (strand ? (int)o0 - 32 : (int)o0 + 64) : 0;
             Oct R0 = ldg256_here(base + o0), R1 = ldg256_here(base + o0 + 32);
+#ifdef CK_S3_OG2
+            // destinations as pointers + a warp-uniform round offset: nothing to update per round
+            uint4 *op[4];
+            _Pragma("unroll") for (u32 i = 0; i < 4; i++) op[i] = reinterpret_cast<uint4 *>(a.out) + og[i];
+#define CK_S3_STORE4 _Pragma("unroll") for (u32 i = 0; i < 4; i++) { if (orem[i] > (int)(4u * s)) op[i][4u * s] = g[i]; }
+#else
+#define CK_S3_STORE4 _Pragma("unroll") for (u32 i = 0; i < 4; i++) { if (orem[i] > 0) reinterpret_cast<uint4 *>(a.out)[og[i]] = g[i]; og[i] += 4; orem[i] -= 4; }
+#endif
 #define CK_T2_SCR(A, I) do { A ^= A >> 47; A ^= sec[16 + I]; A *= CK_P32_1; } while (0)
             // one 64-byte round: chunks W0..W3 of stripe s.  MID: the warp holds records of the XXH3 129..240 form
 #define CK_S3_ROUND(MID)                                                                                            \
@@ -324,16 +342,18 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
                     __syncwarp();                                                                                   \
                     uint4 g[4];                                                                                     \
                     _Pragma("unroll") for (u32 i = 0; i < 4; i++) g[i] = lds128(st_r + 512u * i);                   \
-                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) {                                                 \
-                        if (orem[i] > 0) reinterpret_cast<uint4 *>(a.out)[og[i]] = g[i];                            \
-                        og[i] += 4; orem[i] -= 4;                                                                   \
-                    }                                                                                               \
+                    CK_S3_STORE4                                                                                    \
                     __syncwarp();                                                                                   \
                 }                                                                                                   \
             }
             // two rounds with (LO, UP) = the lower / upper oct of the window.  The round body exists once per instance (a
             // real loop over the two halves): with both instances and the scan loop the hot code stays well inside the
             // instruction cache (a fully unrolled form ran into `no_instructions` stalls: profiles/r02_c_*).
+#ifdef CK_S3_UNROLL_HH
+#define CK_S3_HH_LOOP _Pragma("unroll")
+#else
+#define CK_S3_HH_LOOP _Pragma("unroll 1")
+#endif
 #define CK_S3_PAIR(LO, UP, MID)                                                                                     \
             {                                                                                                       \
                 u32 w[8];                                                                                           \
@@ -356,10 +376,9 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
                     const u8 *ad = base + (u32)min(max(onext, 0), olim);                                            \
                     ldg256_if(LO, ad, strand ^ 1u);                                                                 \
                     ldg256_if(UP, ad, strand);                                                                      \
-                    prefetch_l2(base + (u32)min(max(onext + 6 * ostep, 0), olim));                                  \
                     onext += ostep;                                                                                 \
                 }                                                                                                   \
-                _Pragma("unroll 1") for (u32 hh = 0; hh < 2u && s < rounds; hh++, s++) {                            \
+                CK_S3_HH_LOOP for (u32 hh = 0; hh < 2u && s < rounds; hh++, s++) {                                 \
                     u32 W0, W1, W2, W3;                                                                             \
                     if (hh == 0) { W0 = strand ? w[7] : w[0]; W1 = strand ? w[6] : w[1]; W2 = strand ? w[5] : w[2]; W3 = strand ? w[4] : w[3]; } \
                     else { W0 = strand ? w[3] : w[4]; W1 = strand ? w[2] : w[5]; W2 = strand ? w[1] : w[6]; W3 = strand ? w[0] : w[7]; } \
@@ -386,6 +405,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
             }
 #undef CK_S3_PAIR
 #undef CK_S3_ROUND
+#undef CK_S3_STORE4
             if (want_hash) {
                 // last stripe: canonical bytes [n - 64, n) = D[p0 + n - 64 ..) forward, the mirror of D[p0 + 16 ..) reverse
                 const u32 Bl = strand ? (u32)p0 + 16u : (u32)p0 + nn - 64u;
