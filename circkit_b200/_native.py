@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CIRCKIT_B200_LIB") or os.path.join(HERE, "libcirckit_
 
 CK_OK = 0
 CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5
-CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_PACKED_IN = 1, 2, 4, 8
+CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_PACKED_IN, CK_F_SURVIVORS = 1, 2, 4, 8, 16
 CK_PEER_HANDLE_BYTES = 64
 CK_MONO_SENSITIVE, CK_MONO_FIRST_ONLY, CK_MONO_NONE = 1, 2, 0xFFFFFFFF
 CK_CLASS_2BIT_LE_512, CK_CLASS_2BIT_LE_2048, CK_CLASS_2BIT_LE_65536, CK_CLASS_2BIT_LE_425984 = 1, 2, 4, 8
@@ -45,6 +45,7 @@ SIGNATURES = {
     "ck_canon_wait": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ck_uniq_submit": (_i, [_vp, _i, _vp, _vp, _u32, _u32, _u64]),
     "ck_uniq_wait": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "ck_uniq_wait_survivors": (_i, [_vp, _i, C.POINTER(_u32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ck_uniq_reset": (_i, [_vp]),
     "ck_peer_export": (_i, [_vp, _u32, _u32, _u32, _vp]),
     "ck_peer_attach": (_i, [_vp, _vp]),

@@ -7,8 +7,9 @@ Mirrors src/canonicalize.rs:7-51 and src/uniq.rs:15-88 with the flags of src/com
 the reference keeps on the host -- reading (with the compression sniffing of src/utils.rs:9-27), FASTA record splitting
 (seq_io 0.3.2 rules), writing in the reference's framing (src/canonicalize.rs:33-37, src/uniq.rs:50-61), the duplicate
 table (src/uniq.rs:62-71, src/utils.rs:74-84) and output compression by suffix (src/utils.rs:29-72) -- and hands batches
-of raw record bytes to the C ABI (ck_canon_submit / ck_uniq_submit, two slots in flight), where normalisation, LMSR,
-the canonical form, XXH3-64 and the first-occurrence table run on the GPU.  `--threads` is accepted and ignored.
+of record bytes, packed to 2 bits per base by `--threads` host threads (ck_pack2_host), to the C ABI (ck_*_submit_packed,
+two slots in flight), where LMSR, the canonical form, XXH3-64, the first-occurrence table and the compaction of the
+survivors run on the GPU.  Input and output stream in pieces of 64 MB, so files larger than host memory pass through.
 Nothing is printed on success (tests/canon_uniq.rs:74-77); an I/O error exits non-zero with the OS message on stderr.
 
 Record splitting and output assembly are numpy-vectorised (no per-record Python on the canonicalize path).
@@ -205,6 +206,145 @@ def _assemble(heads: np.ndarray, head_len: np.ndarray, bodies: np.ndarray, body_
     return out.tobytes()
 
 
+# ------------------------------------------------------------------------------------------------ streaming I/O
+CHUNK_BYTES = 64 << 20
+
+
+class _ZstdReader:
+    """streaming zstd decompression through libzstd (no Python module in the image): file-like .read(n)"""
+
+    def __init__(self, f):
+        name = ctypes.util.find_library("zstd") or "libzstd.so.1"
+        self.lib = lib = ctypes.CDLL(name)
+        lib.ZSTD_createDStream.restype = ctypes.c_void_p
+        lib.ZSTD_freeDStream.argtypes = [ctypes.c_void_p]
+        lib.ZSTD_decompressStream.restype = ctypes.c_size_t
+        lib.ZSTD_decompressStream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.ZSTD_isError.restype = ctypes.c_uint
+        lib.ZSTD_isError.argtypes = [ctypes.c_size_t]
+        self.f, self.ds, self.src, self.pos, self.eof = f, lib.ZSTD_createDStream(), b"", 0, False
+
+    def read(self, n: int) -> bytes:
+        class Buf(ctypes.Structure):
+            _fields_ = [("p", ctypes.c_void_p), ("size", ctypes.c_size_t), ("pos", ctypes.c_size_t)]
+        out = ctypes.create_string_buffer(n)
+        ob = Buf(ctypes.cast(out, ctypes.c_void_p), n, 0)
+        while ob.pos < n:
+            if self.pos >= len(self.src):
+                if self.eof:
+                    break
+                self.src, self.pos = self.f.read(1 << 20), 0
+                if not self.src:
+                    self.eof = True
+                    break
+            keep = ctypes.create_string_buffer(self.src, len(self.src))
+            ib = Buf(ctypes.cast(keep, ctypes.c_void_p), len(self.src), self.pos)
+            rc = self.lib.ZSTD_decompressStream(self.ds, ctypes.byref(ob), ctypes.byref(ib))
+            if self.lib.ZSTD_isError(rc):
+                raise OSError("zstd: cannot decompress input")
+            self.pos = ib.pos
+        return out.raw[:ob.pos]
+
+    def close(self):
+        if self.ds:
+            self.lib.ZSTD_freeDStream(self.ds)
+            self.ds = None
+
+
+def iter_input(path: str | None, chunk_bytes: int = CHUNK_BYTES):
+    """src/utils.rs:9-27 as a stream: decompressed chunks of the input (format sniffed from the magic bytes), so that a file
+    far larger than host memory passes through"""
+    if path is None:
+        if sys.stdin.isatty():
+            raise OSError("No input file specified and stdin is a terminal")
+        f = sys.stdin.buffer
+    else:
+        f = open(path, "rb")
+    try:
+        import io
+        head = f.peek(8)[:8] if hasattr(f, "peek") else b""
+        if not head and not hasattr(f, "peek"):
+            f = io.BufferedReader(f)
+            head = f.peek(8)[:8]
+        if head[:2] == b"\x1f\x8b":
+            r = gzip.GzipFile(fileobj=f)
+        elif head[:3] == b"BZh":
+            r = bz2.BZ2File(f)
+        elif head[:6] == b"\xfd7zXZ\x00":
+            r = lzma.LZMAFile(f)
+        elif head[:4] == b"\x28\xb5\x2f\xfd":
+            r = _ZstdReader(f)
+        else:
+            r = f
+        while True:
+            c = r.read(chunk_bytes)
+            if not c:
+                break
+            yield c
+    finally:
+        if path is not None:
+            f.close()
+
+
+class Writer:
+    """src/utils.rs:29-72 as a stream: stdout, or a file compressed by its suffix (gz 6, bz2 9, xz 6, zst 1; else plain)"""
+
+    def __init__(self, path: str | None):
+        self.path, self.zst = path, None
+        if path is None:
+            self.f = sys.stdout.buffer
+            return
+        ext = path.rsplit(".", 1)[-1] if "." in os.path.basename(path) else ""
+        if ext == "gz":
+            self.f = gzip.GzipFile(path, "wb", compresslevel=6)
+        elif ext == "bz2":
+            self.f = bz2.BZ2File(path, "wb", compresslevel=9)
+        elif ext == "xz":
+            self.f = lzma.LZMAFile(path, "wb", preset=6)
+        elif ext == "zst":
+            self.f, self.zst = open(path, "wb"), []          # libzstd one-shot frames: one frame per written piece
+        else:
+            self.f = open(path, "wb")
+
+    def write(self, data: bytes):
+        if not data:
+            return
+        if self.zst is not None:
+            self.f.write(_zstd_compress(data, 1))             # concatenated frames are one valid zstd stream
+        else:
+            self.f.write(data)
+
+    def close(self):
+        if self.path is None:
+            self.f.flush()
+        else:
+            self.f.close()
+
+
+def iter_records(chunks):
+    """Records objects over a stream of chunks: every yield holds whole records only (the tail of a chunk that may belong to
+    an unfinished record is carried into the next one).  seq_io's leading-blank-line rule applies to the first piece only."""
+    carry = b""
+    first = True
+    for c in chunks:
+        data = carry + c if carry else c
+        d = np.frombuffer(data, dtype=np.uint8)
+        gt = np.flatnonzero(d == ord(">"))
+        gt = gt[(gt > 0)]
+        gt = gt[d[gt - 1] == 10]
+        if len(gt) == 0:                                     # no record start after the first byte: keep accumulating
+            carry = data
+            continue
+        cut = int(gt[-1])                                    # the last record of the piece may be unfinished: hold it back
+        piece, carry = data[:cut], data[cut:]
+        if not first and piece[:1] != b">":
+            raise FastaError("expected '>' at record start")
+        first = False
+        yield Records(piece)
+    if carry or first:
+        yield Records(carry)
+
+
 # ------------------------------------------------------------------------------------------------ GPU pump
 MAX_BATCH_BYTES = 256 << 20
 MAX_BATCH_RECORDS = 1 << 20
@@ -226,105 +366,160 @@ def _batches(offsets: np.ndarray):
     return cuts
 
 
-def _pump(ctx: Context, arena: np.ndarray, offsets: np.ndarray, uniq: bool, want_bytes: bool = True):
-    """All batches through the two slots of the C ABI (the bounded queue of parallel_fasta): submit batch b while batch
-    b-1 is collected.  Returns (canonical bytes, normalised lengths, first_index or None), compact layout."""
+def _pump(ctx: Context, arena: np.ndarray, offsets: np.ndarray, uniq: bool, want_bytes: bool = True, base_index: int = 0,
+          threads: int = 0):
+    """All batches of one piece of the input through the two slots of the C ABI (the bounded queue of parallel_fasta): the
+    host packer (ck_pack2_host, `threads` threads) and the submit of batch b run while batch b - 1 is collected.
+    canonicalize -> (canonical bytes of every record, compact; normalised lengths; None; None)
+    uniq         -> (canonical bytes of the SURVIVORS only, compact -- the device compacts them, CK_F_SURVIVORS; lengths;
+                     first_index of every record; indices of the survivors)"""
+    from .core import pack2_host
     n = len(offsets) - 1
     cuts = _batches(offsets)
     lens = np.zeros(n, dtype=np.uint32)
     first = np.zeros(n, dtype=np.uint64) if uniq else None
-    outs = []
+    outs, keeps = [], []
     nb = len(cuts) - 1
+    pend = {}
     for b in range(nb + 1):
         if b < nb:
             lo, hi = cuts[b], cuts[b + 1]
             rel = (offsets[lo: hi + 1] - offsets[lo]).astype(np.uint64)
             sub = arena[int(offsets[lo]): int(offsets[hi])]
+            pb = pack2_host(sub, rel, normalize=True, threads=threads)
             if uniq:
-                ctx.uniq_submit(b & 1, sub, rel, lo, normalize=True, no_bytes=not want_bytes, aligned=True)
+                ctx.uniq_submit_packed(b & 1, pb, base_index + lo, no_bytes=not want_bytes, aligned=True, survivors=True)
             else:
-                ctx.canon_submit(b & 1, sub, rel, normalize=True, aligned=True)
+                ctx.canon_submit_packed(b & 1, pb, aligned=True)
+            pend[b] = pb                                       # keeps the pinned / host arrays alive until the wait
         if b >= 1:
             lo, hi = cuts[b - 1], cuts[b]
-            rel = (offsets[lo: hi + 1] - offsets[lo]).astype(np.uint64)
-            total = int(rel[-1])
+            pb = pend.pop(b - 1)
             if uniq:
-                r = ctx.uniq_wait((b - 1) & 1, hi - lo, total, want_bytes=want_bytes, aligned=True)
+                r = ctx.uniq_wait_survivors((b - 1) & 1, hi - lo, pb.total, want_bytes=want_bytes)
                 first[lo:hi] = r["first"]
+                lens[lo:hi] = r["lens"]
+                idx = r["index"].astype(np.int64)
+                keeps.append(idx + lo)
+                if want_bytes and len(idx):
+                    st = r["offsets"][:-1].astype(np.int64)
+                    outs.append(r["bytes"][_region_mask(len(r["bytes"]), st, st + r["lens"][idx].astype(np.int64))])
             else:
-                r = ctx.canon_wait((b - 1) & 1, hi - lo, total, aligned=True)
-            lens[lo:hi] = r["lens"]
-            if want_bytes:
-                st = ctx.aligned_starts(rel).astype(np.int64)
+                r = ctx.canon_wait((b - 1) & 1, hi - lo, pb.total, aligned=True)
+                lens[lo:hi] = r["lens"]
+                st = ctx.aligned_starts(pb.offsets).astype(np.int64)
                 outs.append(r["out"][_region_mask(len(r["out"]), st, st + r["lens"].astype(np.int64))])
     body = np.concatenate(outs) if outs else np.zeros(0, dtype=np.uint8)
-    return body, lens, first
+    keep = (np.concatenate(keeps) if keeps else np.zeros(0, dtype=np.int64)) if uniq else None
+    return body, lens, first, keep
 
 
-def _context(n_records: int, uniq: bool) -> Context:
-    return Context(max_batch_bytes=MAX_BATCH_BYTES, max_batch_records=MAX_BATCH_RECORDS,
-                   table_capacity=max(n_records, 1) if uniq else 0)
+def _context(table_capacity: int) -> Context:
+    return Context(max_batch_bytes=MAX_BATCH_BYTES, max_batch_records=MAX_BATCH_RECORDS, table_capacity=table_capacity)
+
+
+def _piece_arena(recs: "Records"):
+    seq_len = recs.seq_hi - recs.seq_lo
+    offsets = np.zeros(len(recs) + 1, dtype=np.uint64)
+    np.cumsum(seq_len, out=offsets[1:])
+    return np.ascontiguousarray(recs.gather(recs.seq_lo, recs.seq_hi)), offsets, seq_len
+
+
+def run_canonicalize(pieces, write, threads: int = 0) -> None:
+    """`circkit canonicalize` over a stream of Records pieces (src/canonicalize.rs:7-51); `write(bytes)` gets the output"""
+    ctx = None
+    try:
+        for recs in pieces:
+            if len(recs) == 0:
+                continue
+            if ctx is None:
+                ctx = _context(0)
+            arena, offsets, _ = _piece_arena(recs)
+            body, lens, _, _ = _pump(ctx, arena, offsets, False, threads=threads)
+            heads = recs.gather(recs.head_lo, recs.head_hi)
+            write(_assemble(heads, recs.head_hi - recs.head_lo, body, lens.astype(np.int64)))
+    finally:
+        if ctx is not None:
+            ctx.close()
+
+
+def _check_ids(recs: "Records", which: np.ndarray) -> None:
+    """record.id().unwrap() (src/uniq.rs:48,67): the id -- head up to the first ' ' -- must be UTF-8"""
+    heads = recs.gather(recs.head_lo[which], recs.head_hi[which]).tobytes()
+    try:
+        heads.decode("utf-8")                                 # every head valid => every id valid (the common case)
+        return
+    except UnicodeDecodeError:
+        pass
+    for a, b in zip(recs.head_lo[which].tolist(), recs.head_hi[which].tolist()):
+        recs.data[a:b].tobytes().split(b" ", 1)[0].decode("utf-8")
+
+
+def run_uniq(pieces, write, canonical: bool = False, table_write=None, table_ext: str | None = None, table_capacity: int = 1 << 24,
+             threads: int = 0) -> None:
+    """`circkit uniq` over a stream of Records pieces (src/uniq.rs:15-88): one first-occurrence table on the device for the whole
+    input, survivors written piece by piece in input order, duplicate rows to `table_write` as they are met."""
+    ctx = None
+    base = 0
+    first_ids = {}                                             # global index of a first occurrence -> its id (for --table only)
+    delim = b"\t" if table_ext == "tsv" else b","
+    wrote_header = False
+
+    def field(f: bytes) -> bytes:
+        if any(c in f for c in (delim, b'"', b"\n", b"\r")):
+            return b'"' + f.replace(b'"', b'""') + b'"'
+        return f
+    try:
+        for recs in pieces:
+            n = len(recs)
+            if n == 0:
+                continue
+            if ctx is None:
+                ctx = _context(table_capacity)
+            arena, offsets, seq_len = _piece_arena(recs)
+            body, lens, first, keep_idx = _pump(ctx, arena, offsets, True, want_bytes=canonical, base_index=base, threads=threads)
+            keep = np.zeros(n, dtype=bool)
+            keep[keep_idx] = True                               # first occurrence in input order (src/uniq.rs:47-48)
+            _check_ids(recs, np.ones(n, dtype=bool) if table_write is not None else keep)
+            head_len = (recs.head_hi - recs.head_lo)[keep]
+            heads = recs.gather(recs.head_lo[keep], recs.head_hi[keep])
+            if canonical:                                       # src/uniq.rs:53-56: the device returned the survivors' bytes only
+                bodies, body_len = body, lens.astype(np.int64)[keep]
+            else:                                               # raw record.seq(), internal line breaks included (:57-59)
+                bodies, body_len = recs.gather(recs.seq_lo[keep], recs.seq_hi[keep]), seq_len[keep]
+            write(_assemble(heads, head_len, bodies, body_len))
+            if table_write is not None:                         # src/uniq.rs:62-71, csv 1.2.2 defaults
+                def rec_id(i):
+                    return recs.data[recs.head_lo[i]: recs.head_hi[i]].tobytes().split(b" ", 1)[0]
+                for i in keep_idx.tolist():
+                    first_ids[base + i] = rec_id(i)
+                rows = bytearray()
+                for i in np.flatnonzero(~keep).tolist():
+                    if not wrote_header:
+                        rows += b"id" + delim + b"duplicate_id\n"
+                        wrote_header = True
+                    rows += field(first_ids[int(first[i])]) + delim + field(rec_id(i)) + b"\n"
+                table_write(bytes(rows))
+            base += n
+    finally:
+        if ctx is not None:
+            ctx.close()
 
 
 def canonicalize(fasta: bytes) -> bytes:
     """bytes of a FASTA file -> bytes `circkit canonicalize` writes (src/canonicalize.rs:7-51)"""
-    recs = Records(fasta)
-    if len(recs) == 0:
-        return b""
-    seq_len = recs.seq_hi - recs.seq_lo
-    offsets = np.zeros(len(recs) + 1, dtype=np.uint64)
-    np.cumsum(seq_len, out=offsets[1:])
-    arena = np.ascontiguousarray(recs.gather(recs.seq_lo, recs.seq_hi))
-    ctx = _context(len(recs), False)
-    try:
-        body, lens, _ = _pump(ctx, arena, offsets, False)
-    finally:
-        ctx.close()
-    heads = recs.gather(recs.head_lo, recs.head_hi)
-    return _assemble(heads, recs.head_hi - recs.head_lo, body, lens.astype(np.int64))
+    out = []
+    run_canonicalize(iter_records([fasta] if fasta else []), out.append)
+    return b"".join(out)
 
 
 def uniq(fasta: bytes, canonical: bool = False, table_ext: str | None = None):
     """bytes of a FASTA file -> (bytes `circkit uniq` writes, bytes of the --table file or None) (src/uniq.rs:15-88)"""
-    recs = Records(fasta)
-    table = bytearray() if table_ext is not None else None
-    if len(recs) == 0:
-        return b"", (bytes(table) if table is not None else None)
-    ids = recs.ids()                                        # unwrap()s of src/uniq.rs:48,67 happen for every record
-    seq_len = recs.seq_hi - recs.seq_lo
-    offsets = np.zeros(len(recs) + 1, dtype=np.uint64)
-    np.cumsum(seq_len, out=offsets[1:])
-    arena = np.ascontiguousarray(recs.gather(recs.seq_lo, recs.seq_hi))
-    ctx = _context(len(recs), True)
-    try:
-        body, lens, first = _pump(ctx, arena, offsets, True, want_bytes=canonical)
-    finally:
-        ctx.close()
-    keep = first == np.arange(len(recs), dtype=np.uint64)   # first occurrence in input order (src/uniq.rs:47-48)
-    head_len = (recs.head_hi - recs.head_lo)[keep]
-    heads = recs.gather(recs.head_lo[keep], recs.head_hi[keep])
-    if canonical:                                           # src/uniq.rs:53-56
-        cstart = np.zeros(len(recs) + 1, dtype=np.int64)
-        np.cumsum(lens, out=cstart[1:])
-        bodies = body[_region_mask(len(body), cstart[:-1][keep], cstart[1:][keep])]
-        body_len = lens.astype(np.int64)[keep]
-    else:                                                   # raw record.seq(), internal line breaks included (:57-59)
-        bodies = recs.gather(recs.seq_lo[keep], recs.seq_hi[keep])
-        body_len = seq_len[keep]
-    out = _assemble(heads, head_len, bodies, body_len)
-    if table is not None:                                   # src/uniq.rs:62-71, csv 1.2.2 defaults
-        delim = b"\t" if table_ext == "tsv" else b","
-
-        def field(f: bytes) -> bytes:
-            if any(c in f for c in (delim, b'"', b"\n", b"\r")):
-                return b'"' + f.replace(b'"', b'""') + b'"'
-            return f
-        dups = np.flatnonzero(~keep)
-        if len(dups):
-            table += b"id" + delim + b"duplicate_id\n"
-        for i in dups.tolist():
-            table += field(ids[int(first[i])]) + delim + field(ids[i]) + b"\n"
-    return out, (bytes(table) if table is not None else None)
+    out, table = [], ([] if table_ext is not None else None)
+    n_upper = fasta.count(b">") + 1
+    run_uniq(iter_records([fasta] if fasta else []), out.append, canonical, table.append if table is not None else None, table_ext,
+             table_capacity=n_upper)
+    return b"".join(out), (b"".join(table) if table is not None else None)
 
 
 class CliError(ValueError):
@@ -442,10 +637,9 @@ def main(argv=None) -> int:
     mo.add_argument("--batch-size", type=int, default=64, help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
     try:
-        data = read_input(args.input)
-        if args.command in ("canonicalize", "canon"):
-            write_output(args.output, canonicalize(data))
-        elif args.command == "monomerize":
+        threads = max(1, args.threads or 1)
+        if args.command == "monomerize":
+            data = read_input(args.input)
             ext = None
             if args.table is not None:
                 ext = "tsv" if args.table.endswith(".tsv") else "csv"
@@ -455,15 +649,36 @@ def main(argv=None) -> int:
             if args.table is not None:
                 with open(args.table, "wb") as f:
                     f.write(table)
-        else:
-            ext = None
-            if args.table is not None:
-                ext = "tsv" if args.table.endswith(".tsv") else "csv"
-            out, table = uniq(data, args.canonicalize, ext)
-            write_output(args.output, out)
-            if args.table is not None:
-                with open(args.table, "wb") as f:
-                    f.write(table)
+            return 0
+        # canonicalize / uniq stream: decompress, split, pack, process and write piece by piece (src/utils.rs:9-72)
+        pieces = iter_records(iter_input(args.input))
+        first = next(pieces, None)                              # open the input (and fail on it) before the output is created
+
+        def chain():
+            if first is not None:
+                yield first
+            yield from pieces
+        w = Writer(args.output)
+        tf = None
+        try:
+            if args.command in ("canonicalize", "canon"):
+                run_canonicalize(chain(), w.write, threads=threads)
+            else:
+                ext = None
+                if args.table is not None:
+                    ext = "tsv" if args.table.endswith(".tsv") else "csv"
+                    tf = open(args.table, "wb")
+                cap = 1 << 24
+                if args.input is not None:
+                    # distinct canonical forms the table must hold: bounded by the record count, itself bounded by the input size
+                    # (a record needs >= 4 bytes; compressed DNA rarely beats 4x)
+                    sz = os.path.getsize(args.input)
+                    cap = max(1 << 16, min(1 << 30, sz if args.input.rsplit(".", 1)[-1] in ("gz", "bz2", "xz", "zst") else sz // 4))
+                run_uniq(chain(), w.write, args.canonicalize, tf.write if tf else None, ext, table_capacity=cap, threads=threads)
+        finally:
+            w.close()
+            if tf is not None:
+                tf.close()
     except OSError as e:
         msg = e.strerror or str(e)
         print("Error: %s%s" % (msg, " (os error %d)" % e.errno if e.errno else ""), file=sys.stderr)

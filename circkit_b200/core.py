@@ -172,8 +172,9 @@ class Context:
         st = pb.struct()
         self._check(self._lib.ck_canon_submit_packed(self._h, slot, C.byref(st), flags))
 
-    def uniq_submit_packed(self, slot: int, pb: PackedBatch, base_index: int, *, no_bytes=False, aligned=False):
-        flags = (N.CK_F_NO_BYTES if no_bytes else 0) | (N.CK_F_ALIGNED_OUT if aligned else 0)
+    def uniq_submit_packed(self, slot: int, pb: PackedBatch, base_index: int, *, no_bytes=False, aligned=False, survivors=False):
+        flags = ((N.CK_F_NO_BYTES if no_bytes else 0) | (N.CK_F_ALIGNED_OUT if aligned else 0)
+                 | (N.CK_F_SURVIVORS if survivors else 0))
         st = pb.struct()
         self._check(self._lib.ck_uniq_submit_packed(self._h, slot, C.byref(st), flags, base_index))
 
@@ -191,9 +192,9 @@ class Context:
         return self.uniq_wait(0, pb.n, pb.total, want_bytes=want_bytes, aligned=aligned)
 
     def uniq_submit(self, slot: int, arena: np.ndarray, offsets: np.ndarray, base_index: int, *, normalize: bool,
-                    no_bytes=False, aligned=False):
+                    no_bytes=False, aligned=False, survivors=False):
         flags = ((N.CK_F_NORMALIZE if normalize else 0) | (N.CK_F_NO_BYTES if no_bytes else 0)
-                 | (N.CK_F_ALIGNED_OUT if aligned else 0))
+                 | (N.CK_F_ALIGNED_OUT if aligned else 0) | (N.CK_F_SURVIVORS if survivors else 0))
         self._check(self._lib.ck_uniq_submit(self._h, slot, _ptr(arena), _ptr(offsets), len(offsets) - 1, flags,
                                              base_index))
 
@@ -205,6 +206,21 @@ class Context:
         first = np.zeros(max(n, 1), dtype=np.uint64)
         self._check(self._lib.ck_uniq_wait(self._h, slot, _ptr(out), _ptr(lens), _ptr(h), _ptr(first)))
         return dict(out=None if out is None else out[:nbytes], lens=lens[:n], hash=h[:n], first=first[:n])
+
+    def uniq_wait_survivors(self, slot: int, n: int, total: int, *, want_bytes=True):
+        """ck_uniq_wait_survivors (batch submitted with survivors=True): only what the first occurrences need crosses PCIe.
+        -> dict(n_survivors, index[ns], offsets[ns + 1], bytes (compact arena), lens[n], hash[n], first[n])"""
+        ns = C.c_uint32(0)
+        index = np.zeros(max(n, 1), dtype=np.uint32)
+        offs = np.zeros(max(n, 0) + 1, dtype=np.uint64)
+        out = np.zeros(max(total + 16 * n, 1), dtype=np.uint8) if want_bytes else None
+        lens = np.zeros(max(n, 1), dtype=np.uint32)
+        h = np.zeros(max(n, 1), dtype=np.uint64)
+        first = np.zeros(max(n, 1), dtype=np.uint64)
+        self._check(self._lib.ck_uniq_wait_survivors(self._h, slot, C.byref(ns), _ptr(index), _ptr(offs), _ptr(out), _ptr(lens), _ptr(h),
+                                                     _ptr(first)))
+        k = int(ns.value)
+        return dict(n_survivors=k, index=index[:k], offsets=offs[:k + 1], bytes=out, lens=lens[:n], hash=h[:n], first=first[:n])
 
     def uniq_batch(self, arena: np.ndarray, offsets: np.ndarray, base_index: int = 0, *, normalize: bool = False,
                    want_bytes=True, aligned=False):

@@ -636,6 +636,40 @@ __global__ void k_table_clear(TableSlot *slots, u64 n, u64 *side_first)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Order-preserving compaction of the survivors (src/uniq.rs:47-61: only first occurrences are written, in input
+// order): flags -> cub::DeviceSelect (indices of the survivors, increasing) -> their lengths (rounded up to 16) -> exclusive
+// scan -> gather of the canonical bytes into a compact arena, survivor k at compact_off[k].
+__global__ void __launch_bounds__(256) k_survivor_flags(const u64 *first, u64 base_index, u32 n, u8 *flags)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = first[i] == base_index + i;
+}
+__global__ void __launch_bounds__(256) k_survivor_lens(const u32 *sel, const u32 *n_sel, const u32 *lens, u32 n, u64 *len16)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n) return;
+    len16[k] = k < *n_sel ? (u64)((lens[sel[k]] + 15u) & ~15u) : 0ull;
+}
+__global__ void __launch_bounds__(256) k_gather_survivors(const u32 *sel, const u32 *n_sel, const u32 *lens, const u64 *offsets, const u8 *out,
+                                                          u32 aligned, const u64 *compact_off, u8 *compact)
+{
+    const u32 lane = lane_id();
+    const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const u32 ns = *n_sel;
+    for (u32 k = gw; k < ns; k += nw) {
+        const u32 rec = sel[k], n = lens[rec];
+        const u64 off = offsets[rec];
+        const u8 *src = out + (aligned ? out_byte(off, rec) : off);
+        u8 *dst = compact + compact_off[k];                       // 16-byte aligned
+        if (aligned) {
+            for (u32 c = lane; 16u * c < n; c += 32) reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(src)[c];
+        } else {
+            for (u32 b = lane; b < n; b += 32) dst[b] = src[b];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Hash-range partition for multi-GPU uniq: owner = floor(hash * world / 2^64).  Two passes over
 // the local hashes: counts per owner, then a scatter of (hash, global index) into per-owner runs of the send
 // buffers (order inside a run is free: the owner keeps the minimum index per key).  pos[i] = where record i went, so

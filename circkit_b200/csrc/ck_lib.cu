@@ -11,6 +11,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "../../include/circkit_b200.h"
 #include "ck_kernels.cuh"
@@ -92,6 +94,7 @@ struct Slot {
     u32 *h_counts = nullptr;            // pinned
     ExecScratch scr;
     bool busy = false, uniq = false;
+    u32 *sel = nullptr; u64 *coff = nullptr;    // CK_F_SURVIVORS: survivor indices / compact offsets of the batch in flight
     u32 n = 0, flags = 0; u64 total = 0;
 };
 
@@ -488,6 +491,43 @@ int submit_check(ck_ctx *ctx, int slot, const uint64_t *offsets, uint32_t n_reco
     return CK_OK;
 }
 
+// CK_F_SURVIVORS: compact the batch's survivors on the device (indices, 16-byte-aligned compact offsets, canonical bytes).  The
+// sort workspace of the batch is free by now (stream order): indices | lengths / offsets | flags | cub temporaries live in it;
+// the compact bytes go to the byte arena d_norm (no byte-lane kernel is running any more).
+int enqueue_compaction(ck_ctx *ctx, Slot &s, uint64_t base_index)
+{
+    cudaStream_t st = s.stream;
+    const u32 n = s.n;
+    u8 *w = reinterpret_cast<u8 *>(s.d_lists);
+    u32 *sel = reinterpret_cast<u32 *>(w); w += ((size_t)n * 4 + 255) & ~(size_t)255;
+    u64 *len16 = reinterpret_cast<u64 *>(w); w += ((size_t)(n + 1) * 8 + 255) & ~(size_t)255;
+    u64 *coff = reinterpret_cast<u64 *>(w); w += ((size_t)(n + 1) * 8 + 255) & ~(size_t)255;
+    u8 *flags = w; w += ((size_t)n + 255) & ~(size_t)255;
+    u32 *n_sel = reinterpret_cast<u32 *>(w); w += 256;
+    void *tmp = w;
+    const size_t used = (size_t)(w - reinterpret_cast<u8 *>(s.d_lists));
+    const size_t have = lists_bytes_for(ctx->cfg.max_batch_records);
+    size_t need_a = 0, need_b = 0;
+    cub::CountingInputIterator<u32> ids(0);
+    cub::DeviceSelect::Flagged(nullptr, need_a, ids, flags, sel, n_sel, (int)n, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, need_b, len16, coff, (int)n + 1, st);
+    if (used + std::max(need_a, need_b) > have) return fail(ctx, CK_ERR_ARG, "sort workspace too small for the compaction");
+    size_t tb = have - used;
+    k_survivor_flags<<<(n + 255) / 256, 256, 0, st>>>(s.d_first, base_index, n, flags);
+    CK_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, tb, ids, flags, sel, n_sel, (int)n, st));
+    k_survivor_lens<<<(n + 256) / 256, 256, 0, st>>>(sel, n_sel, s.d_len, n, len16);
+    tb = have - used;
+    CK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tb, len16, coff, (int)n + 1, st));
+    if (!(s.flags & CK_F_NO_BYTES))
+        k_gather_survivors<<<std::min<u32>((n + 7) / 8, 32u * (u32)ctx->num_sms), 256, 0, st>>>(sel, n_sel, s.d_len, s.d_off, s.d_out,
+                                                                                               (s.flags & CK_F_ALIGNED_OUT) ? 1u : 0u, coff, s.d_norm);
+    ctx->launches += 5;
+    CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts + 20, n_sel, 4, cudaMemcpyDeviceToHost, st));
+    s.sel = sel; s.coff = coff;
+    CK_CUDA(ctx, cudaGetLastError());
+    return CK_OK;
+}
+
 // shared back of every submit: the lane formats of the batch are in the slot (d_p2 / d_norm / d_len / d_lane); canonicalise,
 // then (uniq) the first-occurrence table, then the small result copies
 int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
@@ -525,6 +565,10 @@ int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
         CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts + 16, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, st));
     }
     CK_CUDA(ctx, cudaMemcpyAsync(s.h_counts, s.d_counts, 16 * 4, cudaMemcpyDeviceToHost, st));
+    if (s.uniq && (flags & CK_F_SURVIVORS)) {
+        rc = enqueue_compaction(ctx, s, base_index);
+        if (rc) return rc;
+    }
     s.busy = true;
     return CK_OK;
 }
@@ -831,6 +875,42 @@ int ck_dev_peer_first_index(ck_ctx *ctx, void *stream, const uint64_t *hash64, u
     if (!ctx || !table_view(table, table_bytes, slots, nslots, side, ov)) return ctx ? fail(ctx, CK_ERR_ARG, "bad table") : CK_ERR_ARG;
     if (n && (!hash64 || !out_first_index)) return fail(ctx, CK_ERR_ARG, "null argument");
     return peer_first_index(ctx, (cudaStream_t)stream, 0, U(hash64), n, base_index, slots, nslots, side, ov, U(out_first_index), nullptr, nullptr);
+}
+int ck_uniq_wait_survivors(ck_ctx *ctx, int slot, uint32_t *out_n_survivors, uint32_t *out_index, uint64_t *out_compact_offsets,
+                           uint8_t *out_compact_bytes, uint32_t *out_len, uint64_t *out_hash64, uint64_t *out_first_index)
+{
+    if (!ctx) return CK_ERR_ARG;
+    if (slot < 0 || slot > 1) return fail(ctx, CK_ERR_ARG, "slot must be 0 or 1");
+    Slot &s = ctx->slot[slot];
+    if (!s.busy || !s.uniq) return fail(ctx, CK_ERR_STATE, "no matching submit on this slot");
+    if (!out_n_survivors) return fail(ctx, CK_ERR_ARG, "null argument");
+    if (s.n && !(s.flags & CK_F_SURVIVORS)) return fail(ctx, CK_ERR_STATE, "the batch was not submitted with CK_F_SURVIVORS");
+    *out_n_survivors = 0;
+    cudaStream_t st = s.stream;
+    const size_t n = s.n;
+    if (n == 0) return wait_common(ctx, slot, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    // everything that is per record first (same as ck_uniq_wait, without the canonical bytes of all records) ...
+    if (out_len) CK_CUDA(ctx, cudaMemcpyAsync(out_len, s.d_len, n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_hash64) CK_CUDA(ctx, cudaMemcpyAsync(out_hash64, s.d_hash, n * 8, cudaMemcpyDeviceToHost, st));
+    if (out_first_index) CK_CUDA(ctx, cudaMemcpyAsync(out_first_index, s.d_first, n * 8, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
+    s.busy = false;
+    if (s.h_counts[CLS_HUGE]) return fail(ctx, CK_ERR_TOO_LONG, "batch holds a record beyond the staged-length classes");
+    if (s.h_counts[16]) return fail(ctx, CK_ERR_TABLE_FULL, "uniq table is full; raise table_capacity");
+    // ... then what the survivors need, sized by their number
+    const u32 ns = s.h_counts[20];
+    *out_n_survivors = ns;
+    if (ns == 0) return CK_OK;
+    u64 bytes = 0;
+    if (out_index) CK_CUDA(ctx, cudaMemcpyAsync(out_index, s.sel, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaMemcpyAsync(&bytes, s.coff + ns, 8, cudaMemcpyDeviceToHost, st));
+    if (out_compact_offsets) CK_CUDA(ctx, cudaMemcpyAsync(out_compact_offsets, s.coff, ((size_t)ns + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out_compact_bytes && !(s.flags & CK_F_NO_BYTES) && bytes) {
+        CK_CUDA(ctx, cudaMemcpyAsync(out_compact_bytes, s.d_norm, bytes, cudaMemcpyDeviceToHost, st));
+        CK_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return CK_OK;
 }
 int ck_uniq_reset(ck_ctx *ctx)
 {

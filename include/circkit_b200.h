@@ -51,6 +51,7 @@ extern "C" {
                                each record from its aligned start (it copies record by record anyway:
                                src/canonicalize.rs:33-37). */
 
+#define CK_F_SURVIVORS 16u  /* uniq: also compact the survivors on the device, for ck_uniq_wait_survivors */
 #define CK_F_PACKED_IN 8u   /* (set by the *_submit_packed entries) the batch came through ck_pack2_host */
 
 typedef struct ck_ctx ck_ctx;
@@ -86,6 +87,15 @@ int ck_uniq_submit(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *
                    uint32_t n_records, uint32_t flags, uint64_t base_index);
 int ck_uniq_wait(ck_ctx *ctx, int slot, uint8_t *out_bytes, uint32_t *out_len, uint64_t *out_hash64,
                  uint64_t *out_first_index);
+/* The consumer closure writes first occurrences only (src/uniq.rs:47-61).  A batch submitted with CK_F_SURVIVORS is
+ * compacted on the device (flags -> scan -> gather, input order kept), and this wait copies back what the survivors need and
+ * nothing else: *out_n_survivors; out_index[k] = position in the batch of survivor k (increasing); their canonical bytes,
+ * survivor k at out_compact_bytes[out_compact_offsets[k]] (16-byte aligned, out_len[out_index[k]] bytes; out_compact_offsets
+ * has n_survivors + 1 entries, the last one = bytes to expect; skipped with CK_F_NO_BYTES).  out_len / out_hash64 /
+ * out_first_index are per record of the batch as in ck_uniq_wait (the duplicates' rows of --table need them); any may be NULL.
+ * Size out_index for n_records entries, out_compact_offsets for n_records + 1 and out_compact_bytes for offsets[n] + 16 n_records. */
+int ck_uniq_wait_survivors(ck_ctx *ctx, int slot, uint32_t *out_n_survivors, uint32_t *out_index, uint64_t *out_compact_offsets,
+                           uint8_t *out_compact_bytes, uint32_t *out_len, uint64_t *out_hash64, uint64_t *out_first_index);
 int ck_uniq_reset(ck_ctx *ctx);   /* forget every key (new input file) */
 
 /* ---- packed host input: 2 bits per base over PCIe instead of 8 -----------------------------------

@@ -74,3 +74,44 @@ def test_compressed_inputs_are_sniffed(tmp_path):
 def test_missing_input_exits_non_zero(capsys):
     assert cli.main(["canonicalize", "/nonexistent/in.fasta"]) == 1
     assert "No such file or directory" in capsys.readouterr().err       # tests/canon_uniq.rs:8-17
+
+
+def test_streaming_reader_splits_like_the_whole_file_parser(tmp_path):
+    """iter_input + iter_records (pieces of a few hundred bytes) must see exactly the records of a whole-buffer parse, for
+    every hot-path fixture, compressed inputs included, and for records that straddle many pieces"""
+    import random
+    rng = random.Random(4)
+    big = b"".join(b">r%d some description\r\n" % i + b"\n".join(bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(0, 70)))
+                                                                  for _ in range(rng.randint(0, 6))) + b"\n" for i in range(300))
+    cases = {"big": big, "no_final_newline": big[:-1], "leading_blank": b"\n\r\n" + big[:2000]}
+    for d in sorted(os.listdir(FIX)):
+        p = os.path.join(FIX, d, "in.fasta")
+        if os.path.exists(p):
+            cases[d] = open(p, "rb").read()
+    for name, data in cases.items():
+        want = _records(data)
+        for chunk in (7, 64, 1000, 1 << 20):
+            f = tmp_path / "in.fa"
+            f.write_bytes(data)
+            got = []
+            for recs in cli.iter_records(cli.iter_input(str(f), chunk_bytes=chunk)):
+                for a, b, c, e in zip(recs.head_lo, recs.head_hi, recs.seq_lo, recs.seq_hi):
+                    got.append((recs.data[a:b].tobytes(), recs.data[c:e].tobytes()))
+            assert got == want, (name, chunk)
+    plain = open(os.path.join(FIX, "compressed_input", "out.fasta"), "rb").read() if False else None
+    for ext in ("gz", "bz2", "xz", "zst"):
+        p = os.path.join(FIX, "compressed_input", "in.fasta." + ext)
+        data = cli.read_input(p)
+        got = b"".join(cli.iter_input(p, chunk_bytes=13))
+        assert got == data, ext
+
+
+def test_streaming_writer_round_trips_every_suffix(tmp_path):
+    pieces = [b">a\nACGT\n", b"", b">b\n" + b"ACGT" * 5000 + b"\n", b">c\nTTTT\n"]
+    for ext in ("fa", "gz", "bz2", "xz", "zst"):
+        p = str(tmp_path / ("out." + ext))
+        w = cli.Writer(p)
+        for x in pieces:
+            w.write(x)
+        w.close()
+        assert cli.read_input(p) == b"".join(pieces), ext

@@ -97,3 +97,76 @@ def test_packed_and_ascii_paths_agree_on_a_large_batch(ctx):
     starts = ctx.aligned_starts(off).astype(np.int64)
     idx = np.repeat(starts, lens) + (np.arange(int(off[-1])) - np.repeat(off[:-1].astype(np.int64), lens))
     assert np.array_equal(a["out"][idx], b["out"][idx])
+
+
+@pytest.mark.parametrize("aligned", [False, True], ids=["same-offsets", "aligned-arena"])
+@pytest.mark.parametrize("packed", [False, True], ids=["ascii-in", "packed-in"])
+def test_device_compaction_returns_the_survivors_only(ctx, aligned, packed):
+    """CK_F_SURVIVORS / ck_uniq_wait_survivors: the first occurrences (src/uniq.rs:47-61), in input order, with their canonical
+    bytes -- two batches, so that survivors of the second batch depend on the first."""
+    seqs = _records(21, 1800)
+    random.Random(2).shuffle(seqs)
+    arena, off = _batch(seqs)
+    want = oracle.canonicalize_batch(arena, off, normalize=True, threads=8)
+    wh, wfirst = oracle.uniq_consume(want["out"], off, want["lens"])
+    keep = np.nonzero(wfirst == np.arange(len(seqs), dtype=np.uint64))[0]
+    cut = len(seqs) // 3
+    ctx.uniq_reset()
+    got_idx, got_bytes = [], []
+    for k, (lo, hi) in enumerate([(0, cut), (cut, len(seqs))]):
+        o = off[lo: hi + 1] - off[lo]
+        a = arena[int(off[lo]): int(off[hi])]
+        if packed:
+            pb = core.pack2_host(a, o, normalize=True, threads=2)
+            ctx.uniq_submit_packed(k, pb, lo, aligned=aligned, survivors=True)
+        else:
+            ctx.uniq_submit(k, a, o, lo, normalize=True, aligned=aligned, survivors=True)
+        r = ctx.uniq_wait_survivors(k, hi - lo, int(o[-1]))
+        assert np.array_equal(r["first"], wfirst[lo:hi]) and np.array_equal(r["hash"], wh[lo:hi])
+        assert np.array_equal(r["lens"], want["lens"][lo:hi])
+        assert np.all(np.diff(r["index"].astype(np.int64)) > 0)
+        for j, i in enumerate(r["index"]):
+            g = lo + int(i)
+            n = int(want["lens"][g])
+            c0 = int(r["offsets"][j])
+            assert c0 % 16 == 0
+            got_idx.append(g)
+            got_bytes.append(r["bytes"][c0: c0 + n].tobytes())
+    assert got_idx == [int(x) for x in keep]
+    for g, b in zip(got_idx, got_bytes):
+        o0, n = int(off[g]), int(want["lens"][g])
+        assert b == want["out"][o0: o0 + n].tobytes(), g
+
+
+def test_library_drop_ins_from_several_threads(ctx):
+    """lib/src/canonicalize.rs:54 is called from T worker threads (src/canonicalize.rs:21-30): the drop-ins must be safe from
+    several host threads on one context, and fast enough to be called per record."""
+    import threading
+    import time
+    rng = random.Random(9)
+    seqs = [bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(1, 600))) for _ in range(160)] + [b"", b"banana", b"A" * 50]
+    want = [(oracle.canonicalize(s), oracle.lmsr(s), oracle.lmsr_index(s)) for s in seqs]
+    errors = []
+
+    def work(t):
+        try:
+            for i in range(t, len(seqs), 4):
+                assert ctx.canonicalize(seqs[i]) == want[i][0]
+                assert ctx.lmsr(seqs[i]) == want[i][1]
+                assert ctx.lmsr_index(seqs[i]) == want[i][2]
+        except Exception as e:                              # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors[:3]
+    s = seqs[5]
+    ctx.canonicalize(s)
+    lat = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        ctx.canonicalize(s)
+        lat.append(time.perf_counter() - t0)
+    lat.sort()
+    print("single-record ck_canonicalize latency: median %.1f us, p90 %.1f us" % (lat[100] * 1e6, lat[180] * 1e6))
+    assert lat[100] < 200e-6
