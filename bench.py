@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["mono"])
     ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
+    ap.add_argument("--e2e-ascii-every", type=int, default=3,
+                    help="e2e: every k-th batch goes to the device as ASCII (ck_*_submit: the DMA engine moves it while the host threads "
+                         "pack the other batches, ck_pack2_host + ck_*_submit_packed) -- host packing (~70 GB/s of ASCII on 16 threads) and "
+                         "PCIe (~55 GB/s) work side by side instead of one after the other; 0 = every batch packed on the host")
     ap.add_argument("--no-config5", action="store_true", help="default workload only: skip the 100 M-record config-5 sub-record")
     ap.add_argument("--c5-records", type=int, default=100_000_000, help="records of the config-5 sub-record, split over the GPUs")
     ap.add_argument("--overlap", action="store_true",
@@ -387,7 +391,14 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
     pack_flags = 1 if raw else 0
     stats = dict(pack_s=0.0, h2d=0)
 
+    every = max(0, args.e2e_ascii_every)
+
+    def is_ascii(i):
+        return every > 0 and i % every == every - 1
+
     def pack(i):
+        if is_ascii(i):
+            return
         b, s = batches[i], sets[i % 3]
         t0 = time.perf_counter()
         rc = lib.ck_pack2_host(b["bytes_p"], b["off_p"], b["n"], pack_flags, threads, s["dense"], s["lens"], s["lane"], s["lane_bytes"],
@@ -404,7 +415,14 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
 
     def submit(j):                                        # round j: this rank's batch, or an empty one (the rounds are collective)
         i = j if world == 1 else j
-        if i < len(batches):
+        if i < len(batches) and is_ascii(i):
+            b = batches[i]
+            stats["h2d"] += b["total"] + 8 * (b["n"] + 1)
+            if uniq:
+                ctx._check(lib.ck_uniq_submit(ctx.handle, j & 1, b["bytes_p"], b["off_p"], b["n"], sub_flags | pack_flags, b["lo"]))
+            else:
+                ctx._check(lib.ck_canon_submit(ctx.handle, j & 1, b["bytes_p"], b["off_p"], b["n"], sub_flags | pack_flags))
+        elif i < len(batches):
             b, s = batches[i], sets[i % 3]
             if uniq:
                 ctx._check(lib.ck_uniq_submit_packed(ctx.handle, j & 1, C.byref(s["st"]), sub_flags, b["lo"]))
@@ -454,6 +472,68 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # ---- the same path with the packing done beforehand (what a host whose reader threads pack while they parse FASTA --
+    #      the north star's host side -- hands over): the first batches of the input, each in its own packed staging set
+    prepacked = None
+    npre = min(len(batches), 12)
+    if world > 1:                                          # the rounds are collective: every rank takes the same number
+        t = torch.tensor([npre], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        npre = int(t.item())
+    if npre:
+        pre_sets = []
+        for i in range(npre):
+            b = batches[i]
+            words = int(lib.ck_pack2_words(b["total"], b["n"]))
+            ps = dict(dense=lib.ck_alloc_pinned(ctx.handle, 8 * words), lens=lib.ck_alloc_pinned(ctx.handle, 4 * b["n"] + 16),
+                      lane=lib.ck_alloc_pinned(ctx.handle, b["n"] + 16), lane_off=lib.ck_alloc_pinned(ctx.handle, 8 * (b["n"] + 1)),
+                      lane_bytes=lib.ck_alloc_pinned(ctx.handle, (b["total"] if raw else (1 << 16)) + 64),
+                      lane_cap=(b["total"] if raw else (1 << 16)), total=C.c_uint64(0))
+            rc = lib.ck_pack2_host(b["bytes_p"], b["off_p"], b["n"], pack_flags, threads, ps["dense"], ps["lens"], ps["lane"], ps["lane_bytes"],
+                                   ps["lane_cap"], ps["lane_off"], C.byref(ps["total"]))
+            if rc != 0:
+                raise RuntimeError("ck_pack2_host failed: %d" % rc)
+            lt = int(ps["total"].value)
+            ps["st"] = N.CkPackedBatch(ps["dense"], b["off_p"], ps["lens"], ps["lane"], ps["lane_bytes"] if lt else None,
+                                       ps["lane_off"] if lt else None, lt, b["n"])
+            pre_sets.append(ps)
+
+        def pre_step():
+            if uniq:
+                ctx.uniq_reset()
+                if world > 1:
+                    dist.barrier()
+            for j in range(npre + 1):
+                if j < npre:
+                    b = batches[j]
+                    if uniq:
+                        ctx._check(lib.ck_uniq_submit_packed(ctx.handle, j & 1, C.byref(pre_sets[j]["st"]), sub_flags, b["lo"]))
+                    else:
+                        ctx._check(lib.ck_canon_submit_packed(ctx.handle, j & 1, C.byref(pre_sets[j]["st"]), sub_flags))
+                if j >= 1:
+                    wait(j - 1)
+        pre_step()
+        sync_all()
+        tp = time.perf_counter()
+        for _ in range(e2e_steps):
+            pre_step()
+        torch.cuda.synchronize()
+        dtp = time.perf_counter() - tp
+        if world > 1:
+            t = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtp = float(t.item())
+        pre_cnt = torch.tensor([sum(batches[i]["n"] for i in range(npre))], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(pre_cnt)
+        prepacked = {"value": int(pre_cnt.item()) / (dtp / e2e_steps), "unit": "records/s", "records_per_step": int(pre_cnt.item()),
+                     "note": "input already packed (ck_pack2_host outside the timed region): H2D of the 2-bit batches + kernels + D2H"}
+        for ps in pre_sets:
+            for key in ("dense", "lens", "lane", "lane_off", "lane_bytes"):
+                lib.ck_free_pinned(ctx.handle, ps[key])
+        # leave the first-occurrence state of the full run behind for the parity check below
+        e2e_step()
+        torch.cuda.synchronize()
     # ---- parity: first indices of the e2e run == the resident run's (global when world > 1)
     parity = None
     if uniq:
@@ -483,10 +563,13 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
            "records_per_batch": RB,
            "api": ("ck_pack2_host + ck_uniq_submit_packed / ck_uniq_wait" if uniq else "ck_pack2_host + ck_canon_submit_packed / ck_canon_wait")
                   + (" over a peer group (ck_peer_export / ck_peer_attach): global first indices" if world > 1 and uniq else ""),
-           "input": "ASCII record bytes + offsets in pinned host memory; the host packer (%d threads per rank) runs INSIDE the timed region" % threads,
+           "input": "ASCII record bytes + offsets in pinned host memory; the host packer (%d threads per rank) runs INSIDE the timed region%s"
+                    % (threads, "; every %d-th batch crosses PCIe as ASCII and is packed on the device instead, so that the DMA engine and the "
+                                "packer threads work side by side" % every if every else ""),
            "result": "first_index + hash64 + length per record" if uniq else "start + strand + length per record",
            "gbases_per_s": bases_step / (dt / e2e_steps) / 1e9, "records_per_step": rec_step,
            "host_pack_seconds_per_step_rank0": stats["pack_s"], "first_index_parity_with_resident_run": parity,
+           "prepacked": prepacked,
            "note": ("every rank pins its share of the input: the first %d rounds (%d records) of the %d-record input; global uniq over that prefix"
                     % (rounds, rec_step, total_records)) if world > 1 and rec_step < total_records else ""}
     for b in batches:
@@ -664,7 +747,8 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
             config["sharding"] += " [symmetric memory unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
     if w["uniq"] and raw_dev is None:
-        overlap = args.overlap
+        overlap = args.overlap and world > 1
+        slots_1gpu = torch.empty(max(R, 1), dtype=torch.int64, device=dev) if world == 1 else None
         stage_stream = torch.cuda.Stream(device=dev) if overlap else None
         outs_sets = [outs, D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=True, aligned=True) if overlap else outs]
         first_sets = [first, torch.empty_like(first) if overlap else first]
@@ -684,6 +768,13 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
         pipe["k"] += 1
         o_i, f_i = outs_sets[i], first_sets[i]
         cur = torch.cuda.current_stream()
+        if world == 1:
+            # one GPU: canonicalise + hash, then the table passes, straight into this step's result buffer
+            D.canon_packed2(ctx, batch, o_i, ws, class_mask=w["mask"])
+            table.clear()
+            table.insert(o_i.hash[:R], R, slots_1gpu, base_index=base_index)
+            table.first(slots_1gpu, R, f_i)
+            return
         cur.wait_event(pipe["done"][i])             # the stage of step k - 2 has finished with this output set
         D.canon_packed2(ctx, batch, o_i, ws, class_mask=w["mask"])
         pipe["canon"][i].record(cur)
@@ -691,9 +782,7 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
         with torch.cuda.stream(st):
             st.wait_event(pipe["canon"][i])
             table.clear()
-            if world == 1:
-                f_i.copy_(first_fn(o_i.hash[:R], None))
-            elif peer_group is not None:            # exact counts, no padding, nothing to check afterwards
+            if peer_group is not None:              # exact counts, no padding, nothing to check afterwards
                 peer_group.first_index(o_i.hash[:R], base_index, table, f_i)
             elif padded["on"]:
                 # fixed-capacity buckets: no counts to exchange, no host synchronisation in the step; an overflowing bucket is

@@ -88,38 +88,57 @@ __attribute__((target("avx2,bmi2"))) inline uint32_t pack16_bmi2(const uint8_t *
     const uint32_t lo = (uint32_t)_pext_u64(__builtin_bswap64(b), 0x0303030303030303ull);
     return (hi << 16) | lo;
 }
+// 32 A/C/G/T bytes (any case, U) -> two 32-bit units, without leaving the vector registers: 2-bit codes per byte, then
+// c0 * 4 + c1 per byte pair (maddubs), (..) * 16 + (..) per pair of those (madd): one byte of four bases per 32-bit lane,
+// first base in the top bits; a byte shuffle gathers the eight bytes in unit order (bases 0-3 in the unit's top byte).
+__attribute__((target("avx2,bmi2"))) inline void pack32_avx2(__m256i x, uint32_t *dst)
+{
+    const __m256i m3 = _mm256_set1_epi8(3), m1 = _mm256_set1_epi8(1);
+    const __m256i c = _mm256_xor_si256(_mm256_and_si256(_mm256_srli_epi16(x, 1), m3), _mm256_and_si256(_mm256_srli_epi16(x, 2), m1));
+    const __m256i p = _mm256_maddubs_epi16(c, _mm256_set1_epi16(0x0104));          // byte pairs: c0 * 4 + c1
+    const __m256i q = _mm256_madd_epi16(p, _mm256_set1_epi32(0x00010010));         // 16-bit pairs: p0 * 16 + p1 -> low byte of each lane
+    // lanes 0..3 (bases 0-15) -> bytes 3,2,1,0 of the 128-bit half's first word: unit 0 / unit 1 per half
+    const __m256i sh = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                        12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i r = _mm256_shuffle_epi8(q, sh);
+    dst[0] = (uint32_t)_mm256_extract_epi32(r, 0);
+    dst[1] = (uint32_t)_mm256_extract_epi32(r, 4);
+}
 __attribute__((target("avx2,bmi2"))) bool pack_pure_avx2(const uint8_t *s, uint32_t n, uint32_t *dst, bool fold)
 {
     const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
     const __m256i cU = _mm256_set1_epi8('U'), up = _mm256_set1_epi8((char)0xDF);
     uint32_t i = 0;
+    __m256i bad = _mm256_setzero_si256();
     for (; i + 32 <= n; i += 32) {
-        __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i));
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i));
         __m256i ok;
         if (fold) {
-            x = _mm256_and_si256(x, up);       // a-z -> A-Z (other bytes change too, but never INTO the accepted set:
-                                               // 0x61/0x63/0x67/0x74/0x75 are the only bytes that fold onto A/C/G/T/U)
-            ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
-                                 _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT)), _mm256_cmpeq_epi8(x, cU)));
+            const __m256i y = _mm256_and_si256(x, up);   // a-z -> A-Z (other bytes change too, but never INTO the accepted set:
+                                                         // 0x61/0x63/0x67/0x74/0x75 are the only bytes that fold onto A/C/G/T/U)
+            ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(y, cA), _mm256_cmpeq_epi8(y, cC)),
+                                 _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(y, cG), _mm256_cmpeq_epi8(y, cT)), _mm256_cmpeq_epi8(y, cU)));
         } else {
             ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
                                  _mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT)));
         }
-        if ((uint32_t)_mm256_movemask_epi8(ok) != 0xffffffffu) return false;
-        dst[i >> 4] = pack16_bmi2(s + i);
-        dst[(i >> 4) + 1] = pack16_bmi2(s + i + 16);
+        bad = _mm256_or_si256(bad, _mm256_xor_si256(ok, _mm256_set1_epi8(-1)));
+        pack32_avx2(x, dst + (i >> 4));
+        if ((i & 1023u) == 992u && !_mm256_testz_si256(bad, bad)) return false;      // look at the verdict once per KiB
     }
+    if (!_mm256_testz_si256(bad, bad)) return false;
     if (i < n) {
         uint8_t tail[32];
         memset(tail, 'A', 32);
         memcpy(tail, s + i, n - i);
-        uint32_t bad = 0;
-        for (uint32_t k = i; k < n; k++) { const uint8_t m = fold ? kT.norm[s[k]] : s[k]; bad |= (m == 0) | kT.cls[m]; }
-        if (bad) return false;
+        uint32_t b2 = 0;
+        for (uint32_t k = i; k < n; k++) { const uint8_t m = fold ? kT.norm[s[k]] : s[k]; b2 |= (m == 0) | kT.cls[m]; }
+        if (b2) return false;
         const uint32_t r = n - i;
-        uint32_t u0 = pack16_bmi2(tail), u1 = pack16_bmi2(tail + 16);
-        if (r <= 16) { dst[i >> 4] = u0 & ~(r == 16 ? 0u : (0xffffffffu >> (2 * r))); }
-        else { dst[i >> 4] = u0; dst[(i >> 4) + 1] = u1 & ~(r == 32 ? 0u : (0xffffffffu >> (2 * (r - 16)))); }
+        uint32_t u[2];
+        pack32_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(tail)), u);
+        if (r <= 16) { dst[i >> 4] = u[0] & ~(r == 16 ? 0u : (0xffffffffu >> (2 * r))); }
+        else { dst[i >> 4] = u[0]; dst[(i >> 4) + 1] = u[1] & ~(r == 32 ? 0u : (0xffffffffu >> (2 * (r - 16)))); }
     }
     return true;
 }

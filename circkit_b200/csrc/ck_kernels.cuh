@@ -54,6 +54,27 @@ __host__ __device__ constexpr int cls_of_rank(u32 r)
          : r == 6 ? CLS_W4 : r == 7 ? CLS_C4 : r == 8 ? CLS_W8 : r == 9 ? CLS_C8 : r == 10 ? CLS_HUGE : CLS_EMPTY;
 }
 
+// First-occurrence table slot (see "First-occurrence table" below).  (Inserting from inside the kernels that produce the
+// hashes was measured and dropped: the probes' returned atomics stall the latency-sensitive lane kernel -- config 2: 5.68 ->
+// 8.21 ms, config 5: 1.92 -> 4.32 ms -- far more than the separate insert pass costs.)
+struct TableSlot { u64 key; u64 first; };
+#define CK_EMPTY_KEY 0xffffffffffffffffULL
+__device__ __forceinline__ u64 table_home(u64 key, u64 mask) { return (key ^ (key >> 29)) & mask; }
+// CAS the key into its probe sequence, keep the minimum index; returns the slot (~0: the side slot of key == EMPTY,
+// ~0 - 1: table full)
+__device__ __forceinline__ u64 table_insert_one(TableSlot *slots, u64 mask, u64 *side_first, u32 *overflow, u64 key, u64 idx)
+{
+    if (key == CK_EMPTY_KEY) { atomicMin(side_first, idx); return ~0ULL; }
+    u64 s = table_home(key, mask);
+    for (u64 probes = 0; probes <= mask; probes++) {
+        const u64 prev = atomicCAS(&slots[s].key, CK_EMPTY_KEY, key);
+        if (prev == CK_EMPTY_KEY || prev == key) { atomicMin(&slots[s].first, idx); return s; }
+        s = (s + 1) & mask;
+    }
+    *overflow = 1;
+    return ~0ULL - 1;
+}
+
 struct CanonArgs {
     const u64 *packed2;     // 2-bit arena (ck_device.cuh): record i at u64 index p2_word(offsets[i], i)
     const u8 *bytes;        // normalised byte arena: record i at offsets[i]
@@ -586,8 +607,6 @@ __global__ void __launch_bounds__(256) k_scatter_lane_bytes(const u8 *lane_bytes
 // slot = {key, first}; key == EMPTY_KEY marks a free slot, and the one real key equal to EMPTY_KEY is
 // kept in a side slot, so every u64 stays a legal XXH3 value.  Keeping the MIN input index per key
 // reproduces "first record seen wins" of the serial consumer for any insertion order.
-struct TableSlot { u64 key; u64 first; };
-#define CK_EMPTY_KEY 0xffffffffffffffffULL
 struct TableArgs {
     TableSlot *slots; u64 mask;          // capacity - 1 (power of two)
     u64 *side_first;                     // first index of key == EMPTY_KEY
@@ -598,8 +617,6 @@ struct TableArgs {
     u64 *first_out;                      // out (k_table_first)
     u32 *overflow;                       // set if the table is full
 };
-__device__ __forceinline__ u64 table_home(u64 key, u64 mask) { return (key ^ (key >> 29)) & mask; }
-
 __global__ void __launch_bounds__(256) k_table_insert(TableArgs a)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;

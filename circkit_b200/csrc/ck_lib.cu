@@ -541,9 +541,10 @@ int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
+    const bool peer_mode = s.uniq && ctx->peer.attached && ctx->peer.world > 1;
     int rc = run_canon(ctx, st, s.scr, io, 0);
     if (rc) return rc;
-    if (s.uniq && ctx->peer.attached && ctx->peer.world > 1) {
+    if (peer_mode) {
         // multi-GPU: this batch is one of a ROUND of batches, one per rank (include/circkit_b200.h, ck_peer_attach)
         const u32 slot = (u32)(&s - ctx->slot);
         cudaEvent_t prev = (ctx->have_last_insert && ctx->last_insert != s.inserted) ? ctx->last_insert : nullptr;

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
     const u32 count = use_list ? *a.count : a.n_direct;
     if (use_list) a.list += a.count[16];
     const u8 *arena = reinterpret_cast<const u8 *>(a.packed2);
-    const bool pf_scan = !(a.mode & 0x100u), pf_head = !(a.mode & 0x400u);   // CK_S3_DEBUG: L2 prefetches off
+    const bool pf_scan = !(a.mode & 0x100u);   // CK_S3_DEBUG bit 8: L2 prefetch of the scan off
     // request the head of a record (octs 0 and 1, the units of its last scan step) into this lane's head slot, one batch
     // ahead, and the rest of a short record into L2
     auto fetch_head = [&](u64 off1, u32 n1, u32 rec1) {
@@ -69,14 +69,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
         const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
         cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32); cp_async16(head + 48, nb + 48);
         cp_async8(head + 64, nb + 8 * s1); cp_async8(head + 72, nb + 8 * s1 + 8);
-        if (n1 <= 1024u && pf_head) {                              // short records (short batches): both copies -> L2
-            const u32 span = (n1 >> 1) + 48u;
-            if (span > 64u) prefetch_l2(nb + 64);
-            if (span > 128u) prefetch_l2(nb + 128);
-            if (span > 192u) prefetch_l2(nb + 192);
-            if (span > 320u) prefetch_l2(nb + 320);
-            if (span > 448u) prefetch_l2(nb + 448);
-        }
+        // (L2 prefetches of the rest of a short record measured 1-2 % slower on configs 1 and 5: its loads come soon enough)
     };
     const bool has_lens = a.lens != nullptr;
     auto fetch_offsets = [&](u32 rec, u32 slot) {
@@ -157,6 +150,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
         const u32 S1max = __reduce_max_sync(CK_FULL, fast ? S1 : 0u);
         const u32 omax = fast ? ((S1 - 1) >> 2) + 1 : 0u;          // last oct this lane reads
         u32 m1 = 0xffffffffu, m2 = 0xffffffffu;
+        const bool pf_long = pf_scan && S1max >= 32u;             // L2 prefetch ahead of the scan: long records only (+2 % on config 2, -1 % on 1 and 5)
         const uint2 l01 = make_uint2(HT.x, HT.y);
         const u32 l2 = HT.z;
         {
@@ -181,7 +175,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
 #define CK_S3_SCAN(O, O1, O2)                                                                                          \
             {                                                                                                          \
                 O2 = ldg256_here(base + 32 * min(j + CK_S3_AHEAD, omax));                                              \
-                if ((j & 1u) == 0 && pf_scan) prefetch_l2(base + 32 * min(j + 8, omax));                                          \
+                if ((j & 1u) == 0 && pf_long) prefetch_l2(base + 32 * min(j + 8, omax));                                          \
                 const u32 r1 = w2_revcomp(O.lo.y), r2 = w2_revcomp(O.lo.z), r3 = w2_revcomp(O.lo.w);                   \
                 const u32 r4 = w2_revcomp(O.hi.x), r5 = w2_revcomp(O.hi.y), r6 = w2_revcomp(O.hi.z);                   \
                 const u32 r7 = w2_revcomp(O.hi.w), r8 = w2_revcomp(O1.lo.x);                                           \
