@@ -142,6 +142,43 @@ __attribute__((target("avx2,bmi2"))) bool pack_pure_avx2(const uint8_t *s, uint3
     }
     return true;
 }
+// the same 64 bytes at a time (AVX-512 BW + VBMI: one byte permute gathers the sixteen packed bytes in unit order)
+__attribute__((target("avx512f,avx512bw,avx512vbmi,avx2,bmi2"))) bool pack_pure_avx512(const uint8_t *s, uint32_t n, uint32_t *dst, bool fold)
+{
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T');
+    const __m512i cU = _mm512_set1_epi8('U'), up = _mm512_set1_epi8((char)0xDF);
+    const __m512i m3 = _mm512_set1_epi8(3), m1 = _mm512_set1_epi8(1);
+    const __m512i w1 = _mm512_set1_epi16(0x0104), w2 = _mm512_set1_epi32(0x00010010);
+    alignas(64) static const uint8_t idx[64] = {12, 8, 4, 0, 28, 24, 20, 16, 44, 40, 36, 32, 60, 56, 52, 48};
+    const __m512i perm = _mm512_load_si512(idx);
+    uint32_t i = 0;
+    __mmask64 bad = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m512i x = _mm512_loadu_si512(s + i);
+        __mmask64 ok;
+        if (fold) {
+            const __m512i y = _mm512_and_si512(x, up);
+            ok = _mm512_cmpeq_epi8_mask(y, cA) | _mm512_cmpeq_epi8_mask(y, cC) | _mm512_cmpeq_epi8_mask(y, cG) |
+                 _mm512_cmpeq_epi8_mask(y, cT) | _mm512_cmpeq_epi8_mask(y, cU);
+        } else {
+            ok = _mm512_cmpeq_epi8_mask(x, cA) | _mm512_cmpeq_epi8_mask(x, cC) | _mm512_cmpeq_epi8_mask(x, cG) | _mm512_cmpeq_epi8_mask(x, cT);
+        }
+        bad |= ~ok;
+        const __m512i c = _mm512_xor_si512(_mm512_and_si512(_mm512_srli_epi16(x, 1), m3), _mm512_and_si512(_mm512_srli_epi16(x, 2), m1));
+        const __m512i q = _mm512_madd_epi16(_mm512_maddubs_epi16(c, w1), w2);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + (i >> 4)), _mm512_castsi512_si128(_mm512_permutexvar_epi8(perm, q)));
+        if ((i & 1023u) == 960u && bad) return false;
+    }
+    if (bad) return false;
+    if (i < n) return pack_pure_avx2(s + i, n - i, dst + (i >> 4), fold);
+    return true;
+}
+bool have_avx512_vbmi()
+{
+    static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                           __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+    return ok;
+}
 bool have_avx2_bmi2()
 {
     static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
@@ -152,6 +189,7 @@ bool have_avx2_bmi2()
 inline bool pack_pure(const uint8_t *s, uint32_t n, uint32_t *dst, bool fold)
 {
 #if defined(__x86_64__)
+    if (have_avx512_vbmi()) return pack_pure_avx512(s, n, dst, fold);
     if (have_avx2_bmi2()) return pack_pure_avx2(s, n, dst, fold);
 #endif
     return pack_pure_scalar(s, n, dst, fold);

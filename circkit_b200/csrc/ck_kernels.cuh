@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
     if (threadIdx.x < 16 && cnt[threadIdx.x]) atomicAdd(a.counts + threadIdx.x, cnt[threadIdx.x]);
 }
 // run starts of the sorted index list (classes in cls_rank order).  Layout of the 64 counters:
-//   [0, 12)  records per class        [12]  records of the lane-kernel classes together (one launch)
-//   [16, 28) first entry per class    [28]  first entry of the lane-kernel classes
+//   [0, 12)  records per class        [12]  records of the lane-kernel classes together (one launch)   [13] of the long 2-bit classes
+//   [16, 28) first entry per class    [28]  first entry of the lane-kernel classes                     [29] of the long 2-bit classes
 //   [32, 44) retry entries per class  [48, 60)  first retry entry per class (= first entry of the class)
 __global__ void k_list_starts(u32 *counts)
 {
@@ -534,6 +534,8 @@ __global__ void k_list_starts(u32 *counts)
         }
         counts[12] = counts[CLS_W2S] + counts[CLS_W2M] + counts[CLS_W2L] + counts[CLS_W2X];
         counts[28] = counts[16 + CLS_W2S];
+        counts[13] = counts[CLS_C2A] + counts[CLS_C2B];            // the long 2-bit classes together (k_canon_seg)
+        counts[29] = counts[16 + CLS_C2A];
     }
 }
 

@@ -20,6 +20,7 @@
 #include "ck_lane2.cuh"
 #include "ck_stream2.cuh"
 #include "ck_stream3.cuh"
+#include "ck_seg2.cuh"
 #include "ck_synth.cuh"
 #include "ck_monomerize.cuh"
 
@@ -76,6 +77,7 @@ u32 cls_smem_bytes(int c)
 // One set of tie-path scratch buffers: kernels of one in-flight batch use one set.
 struct ExecScratch {
     u32 *tie[CLS_COUNT] = {};
+    u64 *seg = nullptr;                 // k_canon_seg: per-warp partial XXH3 sums
     // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
     // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing.  One set
     // per in-flight batch (slot 0, slot 1, the device-resident API), so batches never queue behind each other's forks.
@@ -133,10 +135,11 @@ struct ck_ctx {
     u64 launches = 0;
     bool attrs_set = false;
     u32 s3_debug = 0;                   // CK_S3_DEBUG: bits 8.. switch the lane kernel's L2 prefetches off (traffic experiments)
+    bool seg_kernel = true;             // CK_SEG_KERNEL=0: long 2-bit records go to the CTA kernels only (A/B runs)
     int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
-    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 3];     // [CLS_COUNT] = lane kernel, then table insert, table first
+    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 4];     // [CLS_COUNT] = lane kernel, table insert, table first, [CLS_COUNT + 3] = segment kernel
 };
 
 namespace {
@@ -197,6 +200,7 @@ int alloc_scratch(ck_ctx *ctx, ExecScratch &s)
         CK_CUDA(ctx, cudaStreamCreateWithFlags(&s.side_stream[c], cudaStreamNonBlocking));
         CK_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_join[c], cudaEventDisableTiming));
     }
+    CK_CUDA(ctx, cudaMalloc(&s.seg, (size_t)2 * ctx->num_sms * CK_SEG_WARPS * CK_SEG_SCRATCH_U64 * 8));
     for (int c = 0; c < CLS_COUNT; c++) {
         if (kCls[c].bits == 0) continue;
         const u64 groups = (u64)kCls[c].ctas_per_sm * ctx->num_sms * (kCls[c].cta ? 1u : kCls[c].threads / 32u);
@@ -213,7 +217,8 @@ void free_scratch(ExecScratch &s)
         s.tie[c] = nullptr; s.side_stream[c] = nullptr; s.ev_join[c] = nullptr;
     }
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-    s.ev_fork = nullptr;
+    if (s.seg) cudaFree(s.seg);
+    s.ev_fork = nullptr; s.seg = nullptr;
 }
 
 template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
@@ -353,6 +358,25 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         CK_CUDA(ctx, timed(CLS_COUNT, e0, e1, false, st));
         ctx->launches++;
     }
+    // long 2-bit records (8 k .. 426 k bases): one warp per record, a lane per segment (ck_seg2.cuh); what ties goes to the
+    // CTA kernels' duel path through the retry lists
+    const u32 seg_classes = (1u << CLS_C2A) | (1u << CLS_C2B);
+    const bool seg_run = fastv && only < 0 && ctx->seg_kernel && (!class_mask || (class_mask & seg_classes));
+    if (seg_run) {
+        CanonArgs a = base_args(CLS_C2A);
+        a.list = sorted; a.count = io.counts + 13; a.n_direct = 0;
+        const u32 g = 2u * (u32)ctx->num_sms, th = 32u * CK_SEG_WARPS, sm = CK_SEG_WARPS * CK_SEG_WARP_BYTES;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        CK_CUDA(ctx, timed(CLS_COUNT + 3, e0, e1, true, st));
+        switch ((a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0)) {
+        case 0: k_canon_seg<0><<<g, th, sm, st>>>(a, scr.seg); break;
+        case 1: k_canon_seg<1><<<g, th, sm, st>>>(a, scr.seg); break;
+        case 2: k_canon_seg<2><<<g, th, sm, st>>>(a, scr.seg); break;
+        default: k_canon_seg<3><<<g, th, sm, st>>>(a, scr.seg); break;
+        }
+        CK_CUDA(ctx, timed(CLS_COUNT + 3, e0, e1, false, st));
+        ctx->launches++;
+    }
     u32 to_launch = 0;
     for (int c = 0; c < CLS_COUNT; c++)
         if (c != CLS_HUGE && !(class_mask && !(class_mask & (1u << c)))) to_launch++;
@@ -364,7 +388,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         if (class_mask && !(class_mask & (1u << c))) continue;
         CanonArgs a = base_args(c);
         const bool is_lane_cls = ((lane_classes >> c) & 1u) != 0;
-        if (lane_run && is_lane_cls) { a.list = retry; a.count = io.counts + 32 + c; a.n_direct = 0; }   // what the lane kernel left over
+        if ((lane_run && is_lane_cls) || (seg_run && ((seg_classes >> c) & 1u))) { a.list = retry; a.count = io.counts + 32 + c; a.n_direct = 0; }   // what the lane / segment kernel left over
         else if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
         else { a.list = sorted; a.count = io.counts + c; a.n_direct = 0; }
         const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
@@ -372,7 +396,9 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         // CTA-per-record kernels fill the GPU by themselves and keep their place on the caller's stream; the warp-per-record
         // launches (retry lists, byte lanes, empty records) are the small ones that gain from running side by side
-        const bool side = fork && !kCls[c].cta;
+        // (behind the segment kernel the CTA kernels of the long 2-bit classes only see its retry list -- the adversarial
+        // repeats -- and no longer fill the GPU: they fork too)
+        const bool side = fork && (!kCls[c].cta || (seg_run && ((seg_classes >> c) & 1u)));
         cudaStream_t sc = side ? scr.side_stream[c] : st;
         if (side) CK_CUDA(ctx, cudaStreamWaitEvent(sc, scr.ev_fork, 0));
         CK_CUDA(ctx, timed(c, e0, e1, true, sc));
@@ -691,6 +717,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
     if (const char *dbg = getenv("CK_S3_DEBUG")) ctx->s3_debug = (u32)strtoul(dbg, nullptr, 0) & 0xff00u;
+    if (const char *sk = getenv("CK_SEG_KERNEL")) ctx->seg_kernel = atoi(sk) != 0;
     if (const char *lk = getenv("CK_LANE_KERNEL")) ctx->lane_kernel = atoi(lk) == 2 ? 2 : 3;
 #define CK_INIT(call)                                                                          \
     do {                                                                                       \
@@ -1293,7 +1320,7 @@ int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_
     if (!ctx || !out_ms || !out_launches) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     CK_CUDA(ctx, cudaDeviceSynchronize());
     for (u32 c = 0; c < n_classes; c++) { out_ms[c] = 0; out_launches[c] = 0; }
-    for (u32 c = 0; c < (u32)CLS_COUNT + 3; c++) {
+    for (u32 c = 0; c < (u32)CLS_COUNT + 4; c++) {
         std::vector<cudaEvent_t> &v = ctx->ev_pairs[c];
         for (size_t k = 0; k + 1 < v.size(); k += 2) {
             float ms = 0;

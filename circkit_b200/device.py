@@ -13,18 +13,19 @@ from . import _native as N
 from .core import Context
 
 CLASS_NAMES = ["2bit_le_512", "2bit_le_2048", "2bit_le_65536", "2bit_le_425984", "4bit_le_2048", "4bit_le_212992",
-               "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192", "2bit_lane_128_8192"]
+               "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192", "2bit_lane_128_8192",
+               "table_insert", "table_first", "2bit_seg_8193_425984"]
 # length range [lo, hi] of each 2-bit class (class_mask bit = index in CLASS_NAMES)
 BYTE_CLASSES = ("4bit_le_2048", "4bit_le_212992", "byte_le_1024", "byte_le_106496")
 CLASS_RANGE = {"2bit_le_512": (1, 512), "2bit_le_2048": (513, 2048), "2bit_le_4096": (2049, 4096), "2bit_le_8192": (4097, 8192),
-               "2bit_le_65536": (8193, 65536), "2bit_le_425984": (65537, 425984), "2bit_lane_128_8192": (1, 8192)}
+               "2bit_le_65536": (8193, 65536), "2bit_le_425984": (65537, 425984), "2bit_lane_128_8192": (1, 8192), "2bit_seg_8193_425984": (8193, 425984)}
 
 
 def class_mask_for(lo: int, hi: int) -> int:
     """class_mask promise for 2-bit records with lengths in [lo, hi]."""
     m = 0
     for name, (a, b) in CLASS_RANGE.items():
-        if "lane" not in name and lo <= b and hi >= a:
+        if "lane" not in name and "seg" not in name and lo <= b and hi >= a:
             m |= 1 << CLASS_NAMES.index(name)
     return m
 

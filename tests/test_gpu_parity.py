@@ -199,6 +199,31 @@ def test_long_records_cta_shape(ctx):
     _check_batch(ctx, seqs, False, tag="long")
 
 
+def test_segment_kernel_lengths_and_rotations(ctx):
+    """k_canon_seg (one warp per record, a lane per segment): lengths around its oct / block / class boundaries, every record
+    also as a rotated and as a reverse-complemented copy (the same canonical form and hash must come back), and records whose
+    minimal 16-mer occurs twice (they take the CTA kernel's duel path)."""
+    rng = random.Random(12)
+    seqs = []
+    for n in [8193, 8200, 8224, 8320, 9000, 12345, 16384, 16385, 20480, 32768, 33000, 65535, 65536, 65537, 65600, 100001, 131072, 150000]:
+        s = _rand_dna(rng, n)
+        r = rng.randrange(n)
+        seqs += [s, s[r:] + s[:r], oracle.revcomp(s[r:] + s[:r])]
+    core = _rand_dna(rng, 20)
+    for n in [9000, 40000]:                                     # the same 20-mer planted twice, and a planted poly-A run
+        s = bytearray(_rand_dna(rng, n, b"CGT"))
+        s[100:120] = b"A" * 20; s[5000:5020] = b"A" * 20
+        seqs.append(bytes(s))
+        s2 = bytearray(_rand_dna(rng, n, b"CGT"))
+        s2[n - 10: n] = b"A" * 10; s2[0:15] = b"A" * 15            # the minimal rotation starts in the record's last bases
+        seqs.append(bytes(s2))
+    _check_batch(ctx, seqs, False, tag="segments", aligned=True)
+    arena, off = _batch(seqs)
+    got = ctx.canonicalize_batch(arena, off, normalize=False, aligned=True)
+    for i in range(0, 54, 3):
+        assert int(got["hash"][i]) == int(got["hash"][i + 1]) == int(got["hash"][i + 2]), i
+
+
 def test_adversarial_long_periodic(ctx):
     rng = random.Random(10)
     seqs = [b"A" * 50000, b"AC" * 40000, _rand_dna(rng, 171) * 300, b"A" * 2000 + _rand_dna(rng, 30000) + b"A" * 1500,
