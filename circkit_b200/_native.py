@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CIRCKIT_B200_LIB") or os.path.join(HERE, "libcirckit_
 
 CK_OK = 0
 CK_ERR_CUDA, CK_ERR_ARG, CK_ERR_STATE, CK_ERR_TOO_LONG, CK_ERR_TABLE_FULL = -1, -2, -3, -4, -5
-CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_PACKED_IN, CK_F_SURVIVORS = 1, 2, 4, 8, 16
+CK_F_NORMALIZE, CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_PACKED_IN, CK_F_SURVIVORS, CK_F_SINGLE_COPY = 1, 2, 4, 8, 16, 32
 CK_PEER_HANDLE_BYTES = 64
 CK_MONO_SENSITIVE, CK_MONO_FIRST_ONLY, CK_MONO_NONE = 1, 2, 0xFFFFFFFF
 CK_CLASS_2BIT_LE_512, CK_CLASS_2BIT_LE_2048, CK_CLASS_2BIT_LE_65536, CK_CLASS_2BIT_LE_425984 = 1, 2, 4, 8
@@ -79,8 +79,9 @@ SIGNATURES = {
     "ck_kernel_timing": (_i, [_vp, _i]),
     "ck_kernel_times": (_i, [_vp, _vp, _vp, _u32]),
     "ck_synth_offsets": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _u32, _u32, _u32, _vp, C.POINTER(_u64)]),
-    "ck_synth_packed2": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp]),
-    "ck_dev_unpack2": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
+    "ck_synth_packed2": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _u32, _u32, _vp, _u32]),
+    "ck_dev_unpack2": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, _u32]),
+    "ck_packed2_words": (_u64, [_u64, _u32, _u32]),
 }
 
 _lib = None

@@ -59,8 +59,19 @@ __device__ __forceinline__ void stab_load()
 // it is stored DOUBLED: units 0 .. (2 n >> 4) + 1 hold the bases S[b mod n] (k_extend_packed2 appends the second copy).
 // Every rotation of the circular record -- and the 128 + 15 bases an output round reads from it -- is then a linear
 // window of the arena: neither the scan nor the emit pass ever wraps.  The host packer only writes the first copy.
-__host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec) { return 4 * ((off >> 6) + 3 * rec); }     // u64 word index
-__host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records) { return 4 * ((total >> 6) + 3 * n_records + 3); }
+// A batch whose 2-bit records are all short (<= 512 bases: viroid lengths, configs 1 and 5) uses the SINGLE-COPY layout
+// instead (dbl == 0): record i at 16-byte granule (offsets[i] >> 6) + 2 i, followed by its circular extension only (units
+// 0 .. (n >> 4) + 4 hold S[b mod n]) -- 113 instead of 258 bytes of arena per 325-base record, everything the emit pass reads
+// is what the scan just read, and the lane kernel of round 1 (ck_stream2.cuh: 128-bit loads, wrap through the extension)
+// takes it.  The layout is a property of the batch: the packer, k_extend_packed2 and every kernel get the same flag.
+__host__ __device__ __forceinline__ u64 p2_word(u64 off, u64 rec, u32 dbl)      // u64 word index
+{
+    return dbl ? 4 * ((off >> 6) + 3 * rec) : 2 * ((off >> 6) + 2 * rec);
+}
+__host__ __device__ __forceinline__ u64 p2_words(u64 total, u64 n_records, u32 dbl = 1)
+{
+    return dbl ? 4 * ((total >> 6) + 3 * n_records + 3) : 2 * ((total >> 6) + 2 * n_records + 2);
+}
 // aligned output arena (CK_F_ALIGNED_OUT): record i's canonical bytes start at byte 32 * ((offsets[i] >> 5) + i).  32 bytes =
 // one DRAM / L2 sector: a 64-byte output round of the lane kernel then covers whole sectors only (with 16-byte alignment half
 // of the records wrote half sectors at both ends of every round, which the memory system pays for with fill reads).

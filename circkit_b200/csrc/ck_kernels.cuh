@@ -76,7 +76,8 @@ __device__ __forceinline__ u64 table_insert_one(TableSlot *slots, u64 mask, u64 
 }
 
 struct CanonArgs {
-    const u64 *packed2;     // 2-bit arena (ck_device.cuh): record i at u64 index p2_word(offsets[i], i)
+    const u64 *packed2;     // 2-bit arena (ck_device.cuh): record i at u64 index p2_word(offsets[i], i, p2_dbl)
+    u32 p2_dbl;             // 1: doubled 32-byte-aligned layout, 0: single copy + extension (batches of short records)
     const u8 *bytes;        // normalised byte arena: record i at offsets[i]
     const u64 *offsets;     // n_records + 1 symbol offsets
     const u32 *lens;        // optional normalised lengths (else offsets[i+1] - offsets[i])
@@ -151,7 +152,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
     const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
     if (a.list == nullptr && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform)
     RecordIn in;
-    in.packed2 = a.packed2 ? a.packed2 + p2_word(off, rec) : nullptr;
+    in.packed2 = a.packed2 ? a.packed2 + p2_word(off, rec, a.p2_dbl) : nullptr;
     in.bytes = a.bytes ? a.bytes + off : nullptr;
     in.n = n;
     stage_record<BITS, G>(in, Xf, Xr);
@@ -233,7 +234,7 @@ __global__ void k_canon_empty(CanonArgs a)
 // bits 1-2 of a byte, which a/A, c/C, g/G, t/T/u/U share); everything else is compacted through a per-warp stage that is
 // laid out congruent to the destination (mod 16 symbols / bytes), so that it leaves as aligned 128-bit pieces.
 struct PrepareArgs {
-    const u8 *raw; const u64 *offsets; u32 n_records; u32 flags;
+    const u8 *raw; const u64 *offsets; u32 n_records; u32 flags;     // flags bit2: doubled packed2 layout
     u64 *packed2; u8 *bytes; u32 *lens; u8 *lane;
 };
 __device__ __forceinline__ u32 code2_of(u32 b) { return ((b >> 1) & 3u) ^ ((b >> 2) & 1u); }   // A,C,G,T -> 0..3
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a)
         const u32 sh = (u32)((size_t)src & 15u);
         const uint4 *src16 = reinterpret_cast<const uint4 *>(src - sh);
         const u32 span = sh + rawlen;                   // bytes from *src16 to the end of the record
-        u32 *dst32 = reinterpret_cast<u32 *>(a.packed2 + p2_word(off, rec));     // 16-base units in address order
+        u32 *dst32 = reinterpret_cast<u32 *>(a.packed2 + p2_word(off, rec, (a.flags >> 2) & 1u));     // 16-base units in address order
         if (cnt == rawlen && pack2) {                    // nothing dropped: pack straight from the raw bytes
             for (u32 base = 0; base < rawlen; base += 512) {
                 const u32 p = base + 16 * lane;
@@ -549,7 +550,7 @@ __global__ void k_list_starts(u32 *counts)
 // while another lane completes it: the bits a reader uses are the same before and after).
 __device__ __forceinline__ u32 p2_last_unit(u32 n) { return max((2u * n + 143u) >> 4, (n >> 4) + 5u); }
 __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane_bits, u32 n_records,
-                                                        const u64 *dense)
+                                                        const u64 *dense, u32 dbl)
 {
     const u32 lane = lane_id();
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -558,9 +559,9 @@ __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 
         const u64 off = offsets[i];
         const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
         if (n == 0) continue;
-        u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i));
+        u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i, dbl));
         const u32 *S = dense ? reinterpret_cast<const u32 *>(dense + (off >> 5) + i) : U;
-        const u32 jn = n >> 4, last = p2_last_unit(n);
+        const u32 jn = n >> 4, last = dbl ? p2_last_unit(n) : jn + 4;          // single copy: the circular extension only
         if (n >= 80) {
             for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
                 const u32 r = (16u * j) % n;                          // first base of the unit, modulo n

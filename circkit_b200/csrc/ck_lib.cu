@@ -96,6 +96,7 @@ struct Slot {
     u32 *h_counts = nullptr;            // pinned
     ExecScratch scr;
     bool busy = false, uniq = false;
+    u32 dbl = 1;                        // packed2 layout of the batch in flight
     u32 *sel = nullptr; u64 *coff = nullptr;    // CK_F_SURVIVORS: survivor indices / compact offsets of the batch in flight
     u32 n = 0, flags = 0; u64 total = 0;
 };
@@ -230,7 +231,7 @@ template <typename K> int set_smem(ck_ctx *ctx, K kernel, u32 bytes)
 // the environment says CK_LANE_KERNEL=2 (A/B runs)
 void s2_launch(ck_ctx *ctx, cudaStream_t st, const CanonArgs &a, int v)
 {
-    if (ctx->lane_kernel != 2) {
+    if (ctx->lane_kernel != 2 && a.p2_dbl) {
         const u32 g3 = 2u * (u32)ctx->num_sms, th3 = 32u * CK_S3_WARPS, sm3 = CK_S3_WARPS * CK_S3_WARP_BYTES;
 #define CK_S3(V) k_canon_s3<V><<<g3, th3, sm3, st>>>(a)
         switch (v) {
@@ -271,6 +272,7 @@ int set_attrs(ck_ctx *ctx)
 struct CanonIO {
     const u64 *packed2; const u8 *bytes; const u64 *offsets; const u32 *lens; const u8 *lane;
     u32 n; u32 mode;
+    u32 dbl = 1;                      // packed2 layout of the batch: 1 doubled (ck_stream3 / ck_seg2), 0 single copy (ck_stream2)
     u8 *out; u32 *out_start; u8 *out_strand; u64 *out_hash;
     u32 *lists; u64 lists_bytes;      // sort workspace: >= ck_lists_bytes(n)
     u32 *counts;                      // 32 u32: class counts, run starts
@@ -337,7 +339,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     };
     auto base_args = [&](int c) {
         CanonArgs a{};
-        a.packed2 = io.packed2; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
+        a.packed2 = io.packed2; a.p2_dbl = io.dbl; a.bytes = io.bytes; a.offsets = io.offsets; a.lens = io.lens;
         a.max_n = cls_max_n(c); a.min_n = cls_min_n(c);
         a.out = io.out; a.out_start = io.out_start; a.out_strand = io.out_strand; a.out_hash = io.out_hash;
         a.scratch = scr.tie[c]; a.scratch_stride = kCls[c].bits ? cls_tie_words(c) : 0;
@@ -361,7 +363,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     // long 2-bit records (8 k .. 426 k bases): one warp per record, a lane per segment (ck_seg2.cuh); what ties goes to the
     // CTA kernels' duel path through the retry lists
     const u32 seg_classes = (1u << CLS_C2A) | (1u << CLS_C2B);
-    const bool seg_run = fastv && only < 0 && ctx->seg_kernel && (!class_mask || (class_mask & seg_classes));
+    const bool seg_run = fastv && only < 0 && ctx->seg_kernel && io.dbl && (!class_mask || (class_mask & seg_classes));
     if (seg_run) {
         CanonArgs a = base_args(CLS_C2A);
         a.list = sorted; a.count = io.counts + 13; a.n_direct = 0;
@@ -509,11 +511,14 @@ int submit_check(ck_ctx *ctx, int slot, const uint64_t *offsets, uint32_t n_reco
     if (offsets[0] != 0) return fail(ctx, CK_ERR_ARG, "offsets[0] must be 0");
     const u64 total = offsets[n_records];
     if (total > ctx->cfg.max_batch_bytes) return fail(ctx, CK_ERR_ARG, "batch exceeds max_batch_bytes");
+    u64 longest = 0;
     for (u32 i = 0; i < n_records; i++) {
         if (offsets[i + 1] < offsets[i]) return fail(ctx, CK_ERR_ARG, "offsets must be non-decreasing");
-        if (offsets[i + 1] - offsets[i] > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
+        longest = std::max<u64>(longest, offsets[i + 1] - offsets[i]);
     }
+    if (longest > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
     s.total = total;
+    s.dbl = longest > 512 ? 1u : 0u;     // batches of short records: single-copy arena (ck_device.cuh)
     return CK_OK;
 }
 
@@ -563,7 +568,7 @@ int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
     CanonIO io{};
     // without normalisation every byte is a symbol: lengths are the offset differences and the lane-per-record kernel applies
     io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = lens_given ? s.d_len : nullptr; io.lane = s.d_lane;
-    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
+    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u; io.dbl = s.dbl;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
@@ -628,9 +633,9 @@ int submit_common(ck_ctx *ctx, int slot, const uint8_t *bytes, const uint64_t *o
     CK_CUDA(ctx, cudaSetDevice(ctx->device));
     CK_CUDA(ctx, cudaMemcpyAsync(s.d_off, offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
     if (total) CK_CUDA(ctx, cudaMemcpyAsync(s.d_raw, bytes, total, cudaMemcpyHostToDevice, st));
-    PrepareArgs pa{s.d_raw, s.d_off, n_records, flags & CK_F_NORMALIZE, s.d_p2, s.d_norm, s.d_len, s.d_lane};
+    PrepareArgs pa{s.d_raw, s.d_off, n_records, (flags & CK_F_NORMALIZE) | (s.dbl << 2), s.d_p2, s.d_norm, s.d_len, s.d_lane};
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
-    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, nullptr);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, nullptr, s.dbl);
     ctx->launches += 2;
     return submit_tail(ctx, s, (flags & CK_F_NORMALIZE) != 0, base_index);
 }
@@ -655,7 +660,7 @@ int submit_packed(ck_ctx *ctx, int slot, const ck_packed_batch *b, uint32_t flag
     CK_CUDA(ctx, cudaMemcpyAsync(s.d_len, b->lens, (size_t)n_records * 4, cudaMemcpyHostToDevice, st));
     CK_CUDA(ctx, cudaMemcpyAsync(s.d_lane, b->lane, (size_t)n_records, cudaMemcpyHostToDevice, st));
     CK_CUDA(ctx, cudaMemcpyAsync(s.d_dense, b->packed2, (size_t)ck_pack2_words(s.total, n_records) * 8, cudaMemcpyHostToDevice, st));
-    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, s.d_dense);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(s.d_p2, s.d_off, s.d_len, s.d_lane, n_records, s.d_dense, s.dbl);
     ctx->launches++;
     if (b->lane_bytes_total) {
         CK_CUDA(ctx, cudaMemcpyAsync(s.d_laneoff, b->lane_offsets, (size_t)(n_records + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1040,9 +1045,9 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     u32 h_counts[16] = {};
     CK_CUDA(ctx, cudaMemcpyAsync(d + o_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice, st));
     if (total) CK_CUDA(ctx, cudaMemcpyAsync(d + o_raw, bytes, total, cudaMemcpyHostToDevice, st));
-    PrepareArgs pa{d + o_raw, (u64 *)(d + o_off), n_records, 0u, (u64 *)(d + o_p2), d + o_norm, (u32 *)(d + o_len), d + o_lane};
+    PrepareArgs pa{d + o_raw, (u64 *)(d + o_off), n_records, 1u << 2, (u64 *)(d + o_p2), d + o_norm, (u32 *)(d + o_len), d + o_lane};
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
-    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>((u64 *)(d + o_p2), (u64 *)(d + o_off), (u32 *)(d + o_len), d + o_lane, n_records, nullptr);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>((u64 *)(d + o_p2), (u64 *)(d + o_off), (u32 *)(d + o_len), d + o_lane, n_records, nullptr, 1u);
     ctx->launches += 2;
     CanonIO io{};
     io.packed2 = (u64 *)(d + o_p2); io.bytes = d + o_norm; io.offsets = (u64 *)(d + o_off); io.lens = (u32 *)(d + o_len); io.lane = d + o_lane;
@@ -1102,7 +1107,7 @@ int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, con
     if (!ctx) return CK_ERR_ARG;
     if (workspace_bytes < ck_dev_workspace_bytes(n_records, 0)) return fail(ctx, CK_ERR_ARG, "workspace too small");
     CanonIO io{};
-    io.packed2 = U(packed2); io.offsets = U(offsets); io.n = n_records;
+    io.packed2 = U(packed2); io.offsets = U(offsets); io.n = n_records; io.dbl = (flags & CK_F_SINGLE_COPY) ? 0u : 1u;
     io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand; io.out_hash = U(out_hash64);
     io.counts = (u32 *)workspace; io.lists = (u32 *)((u8 *)workspace + 256); io.lists_bytes = lists_bytes_for(n_records);
@@ -1134,9 +1139,9 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     u8 *norm = w; w += (total_bytes + 63) & ~63ull;
     u8 *lane = w;
     cudaStream_t st = (cudaStream_t)stream;
-    PrepareArgs pa{bytes, U(offsets), n_records, flags & CK_F_NORMALIZE, p2, norm, out_len, lane};
+    PrepareArgs pa{bytes, U(offsets), n_records, (flags & CK_F_NORMALIZE) | (1u << 2), p2, norm, out_len, lane};
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
-    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records, nullptr);
+    k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records, nullptr, 1u);
     ctx->launches += 2;
     CanonIO io{};
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
@@ -1282,7 +1287,7 @@ int ck_dev_normalize(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint
     if (!ctx) return CK_ERR_ARG;
     if (!n_records) return CK_OK;
     if (!offsets || !out_bytes || !out_len) return fail(ctx, CK_ERR_ARG, "null argument");
-    PrepareArgs pa{bytes, U(offsets), n_records, 1u | 2u, nullptr, out_bytes, out_len, nullptr};
+    PrepareArgs pa{bytes, U(offsets), n_records, 1u | 2u | 4u, nullptr, out_bytes, out_len, nullptr};
     k_prepare<<<ctx->num_sms * 32, 256, 0, (cudaStream_t)stream>>>(pa);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
@@ -1356,23 +1361,31 @@ int ck_synth_offsets(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_in
     if (total_out_host) *total_out_host = total;
     return CK_OK;
 }
-int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
-                     const uint64_t *offsets_dev, uint32_t dup_permille, uint32_t adversarial_permille, uint64_t *packed2_dev)
+uint64_t ck_packed2_words(uint64_t total_bytes, uint32_t n_records, uint32_t flags)
 {
+    return p2_words(total_bytes, n_records, (flags & CK_F_SINGLE_COPY) ? 0u : 1u);
+}
+int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
+                     const uint64_t *offsets_dev, uint32_t dup_permille, uint32_t adversarial_permille, uint64_t *packed2_dev,
+                     uint32_t flags)
+{
+    const u32 dbl = (flags & CK_F_SINGLE_COPY) ? 0u : 1u;
     if (!ctx || !offsets_dev || !packed2_dev) return ctx ? fail(ctx, CK_ERR_ARG, "bad synth arguments") : CK_ERR_ARG;
     SynthArgs a{seed, n_records, 0, 0, 0, dup_permille, adversarial_permille, first_index};
     if (n_records) {
-        k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev));
-        k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, (cudaStream_t)stream>>>(U(packed2_dev), U(offsets_dev), nullptr, nullptr, n_records, nullptr);
+        k_synth_packed2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(a, U(offsets_dev), U(packed2_dev), dbl);
+        k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, (cudaStream_t)stream>>>(U(packed2_dev), U(offsets_dev), nullptr, nullptr, n_records, nullptr, dbl);
     }
     ctx->launches += 2;
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }
-int ck_dev_unpack2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records, uint8_t *ascii_out)
+int ck_dev_unpack2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records, uint8_t *ascii_out,
+                   uint32_t flags)
 {
     if (!ctx) return CK_ERR_ARG;
-    if (n_records) k_unpack2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(U(packed2), U(offsets), n_records, ascii_out);
+    if (n_records) k_unpack2<<<ctx->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(U(packed2), U(offsets), n_records, ascii_out,
+                                                                                 (flags & CK_F_SINGLE_COPY) ? 0u : 1u);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(32 * CK_SEG_WARPS, 2) k_canon_seg(CanonArgs a,
         const u32 rec = a.list[e];
         const u64 off = a.offsets[rec];
         const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
-        const u8 *base = arena + 8ull * p2_word(off, rec);
+        const u8 *base = arena + 8ull * p2_word(off, rec, 1u);
         u8 *dst = want_out ? a.out + out_byte(off, rec) : nullptr;
 
         // ---- scan: lane l owns the octs [o0, o1) = the steps [4 o0, 4 o1); step S1 is the record's partial one

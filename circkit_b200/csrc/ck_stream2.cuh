@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
     // request the head of a record (quads 0..2 and the three units of its last scan step) into this lane's head slot: issued
     // one batch ahead, so no lane waits for the first touch of its record
     auto fetch_head = [&](u64 off1, u32 n1, u32 rec1) {
-        const u8 *nb = arena + 8ull * p2_word(off1, rec1);
+        const u8 *nb = arena + 8ull * p2_word(off1, rec1, a.p2_dbl);
         const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
         cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32);
         cp_async8(head + 48, nb + 8 * s1); cp_async8(head + 56, nb + 8 * s1 + 8);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         // lane-private fast path: n >= 128 (with a hash: n >= 129, the 129..240 and the long XXH3 forms)
         bool fast = in_class && n >= (want_hash ? 129u : 128u);
-        const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record: units 0 .. jn + 4 are valid
+        const u8 *base = arena + 8ull * p2_word(off, rec, a.p2_dbl);         // this lane's record: units 0 .. jn + 4 are valid
         u8 *dst = want_out ? a.out + out_byte(off, rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
         u64 h = 0;
@@ -270,8 +270,12 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                     orem[i] = (int)__shfl_sync(CK_FULL, nchunks, 8 * i + (lane >> 2)) - (int)(lane & 3u);
                 }
             }
-            const u32 ost = aux + 80u * lane;                      // this lane's 64 bytes in the stage (stride 80: no conflicts)
-            const u32 ord = aux + 80u * (lane >> 2) + 16u * (lane & 3u);
+            // output stage, conflict-free for the writes (lane = row) and the reads (4 lanes = one row): row r, chunk c ->
+            // 128-byte line r >> 1, 16-byte slot (c + 4 (r & 1) + ((r >> 1) & 3)) & 7 (ck_stream3.cuh)
+            const u32 st_w = aux + 128u * (lane >> 1), st_j = 4u * (lane & 1u) + ((lane >> 1) & 3u);
+            const u32 st_w0 = st_w + 16u * (st_j & 7u), st_w1 = st_w + 16u * ((st_j + 1u) & 7u);
+            const u32 st_w2 = st_w + 16u * ((st_j + 2u) & 7u), st_w3 = st_w + 16u * ((st_j + 3u) & 7u);
+            const u32 st_r = aux + 128u * (lane >> 3) + 16u * (((lane & 3u) + 4u * ((lane >> 2) & 1u) + ((lane >> 3) & 3u)) & 7u);
             const u64 *sec = reinterpret_cast<const u64 *>(c_secret);
             // the two quads of a round and its (unit offset, bit shift), in two register sets: the next round's are requested
             // into the other set before this round's are used (the loop is unrolled twice, so nothing is ever moved)
@@ -329,10 +333,10 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                     }                                                                                               \
                 }                                                                                                   \
                 if (want_out) {                                                                                     \
-                    sts128(ost, v[0]); sts128(ost + 16, v[1]); sts128(ost + 32, v[2]); sts128(ost + 48, v[3]);      \
+                    sts128(st_w0, v[0]); sts128(st_w1, v[1]); sts128(st_w2, v[2]); sts128(st_w3, v[3]);             \
                     __syncwarp();                                                                                   \
                     uint4 g[4];                                                                                     \
-                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) g[i] = lds128(ord + 640u * i);                    \
+                    _Pragma("unroll") for (u32 i = 0; i < 4; i++) g[i] = lds128(st_r + 512u * i);                   \
                     _Pragma("unroll") for (u32 i = 0; i < 4; i++) {                                                 \
                         if (orem[i] > 0) reinterpret_cast<uint4 *>(a.out)[og[i]] = g[i];                            \
                         og[i] += 4; orem[i] -= 4;                                                                   \

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
     // request the head of a record (octs 0 and 1, the units of its last scan step) into this lane's head slot, one batch
     // ahead, and the rest of a short record into L2
     auto fetch_head = [&](u64 off1, u32 n1, u32 rec1) {
-        const u8 *nb = arena + 8ull * p2_word(off1, rec1);
+        const u8 *nb = arena + 8ull * p2_word(off1, rec1, 1u);
         const u32 s1 = n1 >= 128u ? ((n1 + 31u) >> 5) - 1u : 0u;
         cp_async16(head, nb); cp_async16(head + 16, nb + 16); cp_async16(head + 32, nb + 32); cp_async16(head + 48, nb + 48);
         cp_async8(head + 64, nb + 8 * s1); cp_async8(head + 72, nb + 8 * s1 + 8);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
         bool fast = in_class && n >= (want_hash ? 129u : 128u);
-        const u8 *base = arena + 8ull * p2_word(off, rec);         // this lane's record, doubled
+        const u8 *base = arena + 8ull * p2_word(off, rec, 1u);         // this lane's record, doubled
         u8 *dst = want_out ? a.out + out_byte(off, rec) : nullptr;
         u32 os = 0;                                                // (start << 1) | strand, strand's own coordinates
         u64 h = 0;

@@ -75,7 +75,7 @@ __global__ void k_synth_lens(SynthArgs a, u64 *lens_out)
 }
 
 // one warp per record, one lane per output word
-__global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *offsets, u64 *packed2)
+__global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *offsets, u64 *packed2, u32 dbl)
 {
     const u32 lane = threadIdx.x & 31u;
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *o
         const u64 gi = a.first_index + i;
         const u64 off = offsets[i];
         const u32 n = (u32)(offsets[i + 1] - off);
-        u64 *dst = packed2 + p2_word(off, i);
+        u64 *dst = packed2 + p2_word(off, i, dbl);
         const u64 o = synth_origin(a.seed, gi, a.dup_permille);
         const bool dup = o != gi;
         const u32 W = (n + 31) >> 5;
@@ -117,14 +117,14 @@ __global__ void __launch_bounds__(256) k_synth_packed2(SynthArgs a, const u64 *o
 }
 
 // 2-bit arena -> ASCII arena
-__global__ void __launch_bounds__(256) k_unpack2(const u64 *packed2, const u64 *offsets, u32 n_records, u8 *out)
+__global__ void __launch_bounds__(256) k_unpack2(const u64 *packed2, const u64 *offsets, u32 n_records, u8 *out, u32 dbl)
 {
     const u32 lane = threadIdx.x & 31u;
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (u32 i = gw; i < n_records; i += nw) {
         const u64 off = offsets[i];
         const u32 n = (u32)(offsets[i + 1] - off);
-        const u64 *src = packed2 + p2_word(off, i);
+        const u64 *src = packed2 + p2_word(off, i, dbl);
         for (u32 t = lane; t < n; t += 32) {
             u32 c = (reinterpret_cast<const u32 *>(src)[t >> 4] >> (30 - 2 * (t & 15))) & 3u;
             out[off + t] = "ACGT"[c];

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
         if (pipelined && e + nw < count) {                                                                           \
             const u32 nn = end_n - (u32)off_n;                                                                       \
             if (lane < ((nn + 31) >> 5))                                                                             \
-                d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + p2_word(off_n, rec_n)) + lane);             \
+                d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + p2_word(off_n, rec_n, a.p2_dbl)) + lane);             \
         }                                                                                                            \
     } while (0)
     if (pipelined && e < count) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
         if (use_list && e + nw < count) rec_nn = a.list[e + nw];
         off_n = a.offsets[rec_n]; end_n = (u32)a.offsets[rec_n + 1];
         const u32 nn = end_n - (u32)off_n;
-        if (lane < ((nn + 31) >> 5)) d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + p2_word(off_n, rec_n)) + lane);
+        if (lane < ((nn + 31) >> 5)) d_n = __ldg(reinterpret_cast<const uint2 *>(a.packed2 + p2_word(off_n, rec_n, a.p2_dbl)) + lane);
     }
     for (; e < count; e += nw) {
         u32 rec; u64 off; u32 n; uint2 d0 = make_uint2(0, 0);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256, 4) k_canon_w2(CanonArgs a)
             n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
         }
         const bool in_range = use_list || (n >= a.min_n && n <= a.max_n);    // direct mode: k_classify reported the rest
-        const u64 *src = a.packed2 + p2_word(off, rec);
+        const u64 *src = a.packed2 + p2_word(off, rec, a.p2_dbl);
         u8 *dst = want_out ? a.out + (aligned_out ? out_byte(off, rec) : off) : nullptr;
         u32 os = 0;                                               // (start << 1) | strand of the canonical rotation
         u64 h = 0;

@@ -41,8 +41,13 @@ def _p(t):
 class DeviceBatch:
     """A packed 2-bit batch resident in HBM: offsets[int64, n+1], packed2[int64 words]."""
 
-    def __init__(self, offsets: torch.Tensor, packed2: torch.Tensor, n_records: int, total: int):
+    def __init__(self, offsets: torch.Tensor, packed2: torch.Tensor, n_records: int, total: int, single: bool = False):
         self.offsets, self.packed2, self.n, self.total = offsets, packed2, n_records, total
+        self.single = single        # CK_F_SINGLE_COPY: the single-copy arena layout (batches of records <= 512 bases)
+
+    @property
+    def layout_flag(self) -> int:
+        return N.CK_F_SINGLE_COPY if self.single else 0
 
     @property
     def lens(self) -> torch.Tensor:
@@ -50,18 +55,22 @@ class DeviceBatch:
 
 
 def synth_batch(ctx: Context, *, seed: int, first_index: int, n_records: int, kind: int, lo: int, hi: int,
-                dup_permille: int = 0, adversarial_permille: int = 0, device=None) -> DeviceBatch:
-    """BASELINE.json synthetic records generated straight into the packed arena."""
+                dup_permille: int = 0, adversarial_permille: int = 0, device=None, single: bool | None = None) -> DeviceBatch:
+    """BASELINE.json synthetic records generated straight into the packed arena.  single: the single-copy layout
+    (default: chosen like the host-buffer entries do -- batches whose records are all <= 512 bases)."""
+    if single is None:
+        single = hi <= 512
+    lf = N.CK_F_SINGLE_COPY if single else 0
     dev = device or torch.device("cuda", ctx.device)
     offsets = torch.empty(n_records + 1, dtype=torch.int64, device=dev)
     total = C.c_uint64(0)
     ctx._check(ctx._lib.ck_synth_offsets(ctx.handle, _stream(), seed, first_index, n_records, kind, lo, hi,
                                          dup_permille, _p(offsets), C.byref(total)))
-    words = 4 * ((total.value >> 6) + 3 * n_records + 3)       # ck_device.cuh: p2_words
+    words = int(ctx._lib.ck_packed2_words(total.value, n_records, lf))
     packed2 = torch.empty(words, dtype=torch.int64, device=dev)
     ctx._check(ctx._lib.ck_synth_packed2(ctx.handle, _stream(), seed, first_index, n_records, _p(offsets),
-                                         dup_permille, adversarial_permille, _p(packed2)))
-    return DeviceBatch(offsets, packed2, n_records, total.value)
+                                         dup_permille, adversarial_permille, _p(packed2), lf))
+    return DeviceBatch(offsets, packed2, n_records, total.value, single)
 
 
 def unpack_ascii(ctx: Context, b: DeviceBatch, n_records: int | None = None) -> torch.Tensor:
@@ -69,7 +78,7 @@ def unpack_ascii(ctx: Context, b: DeviceBatch, n_records: int | None = None) -> 
     n = b.n if n_records is None else n_records
     total = int(b.offsets[n].item())
     out = torch.empty(max(total, 1), dtype=torch.uint8, device=b.offsets.device)
-    ctx._check(ctx._lib.ck_dev_unpack2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), n, _p(out)))
+    ctx._check(ctx._lib.ck_dev_unpack2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), n, _p(out), b.layout_flag))
     return out[:total]
 
 
@@ -91,7 +100,7 @@ class Workspace:
 
 def canon_packed2(ctx: Context, b: DeviceBatch, outs: CanonOutputs, ws: Workspace, class_mask: int = 0):
     """k_classify + LMSR/canonical/XXH3 kernels over a resident batch (no copies, no sync)."""
-    flags = (N.CK_F_ALIGNED_OUT if outs.aligned else 0) | (0 if outs.out is not None else N.CK_F_NO_BYTES)
+    flags = (N.CK_F_ALIGNED_OUT if outs.aligned else 0) | (0 if outs.out is not None else N.CK_F_NO_BYTES) | b.layout_flag
     ctx._check(ctx._lib.ck_dev_canon_packed2(ctx.handle, _stream(), _p(b.packed2), _p(b.offsets), b.n, flags, class_mask,
                                              _p(outs.out), _p(outs.start), _p(outs.strand), _p(outs.hash),
                                              _p(ws.buf), ws.bytes))

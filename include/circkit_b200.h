@@ -52,6 +52,7 @@ extern "C" {
                                src/canonicalize.rs:33-37). */
 
 #define CK_F_SURVIVORS 16u  /* uniq: also compact the survivors on the device, for ck_uniq_wait_survivors */
+#define CK_F_SINGLE_COPY 32u /* device-resident API: the packed2 arena is in the single-copy layout (batches of records <= 512 bases) */
 #define CK_F_PACKED_IN 8u   /* (set by the *_submit_packed entries) the batch came through ck_pack2_host */
 
 typedef struct ck_ctx ck_ctx;
@@ -162,11 +163,16 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
  * All pointers are device pointers, `stream` is a cudaStream_t (0 = default stream).  Nothing is copied
  * and nothing synchronises; call ck_dev_check() once a stream's work matters.
  * packed2: 2-bit arena, A,C,G,T = 0..3, 16 bases per 32-bit unit with the first base in the top bits, units in
- * address order; record i starts at byte 32 * ((offsets[i] >> 6) + 3 i) and is stored DOUBLED (units 0 .. (2 n + 143) >> 4,
- * at least (n >> 4) + 5, hold the bases S[b mod n]), so that every rotation of the circular record is a linear window;
- * the arena holds 4 * (total/64 + 3 n_records + 3) 64-bit words.  class_mask: 0 = any record; else a promise about the
- * batch (bit c set = length/alphabet class c may occur, see CK_CLASS_*), which skips the launches of absent classes;
- * records outside the promise are reported by ck_dev_check(), never silently dropped. */
+ * address order.  Two layouts, a property of the batch (ck_packed2_words() gives the arena size in 64-bit words):
+ *   doubled (default)      record i starts at byte 32 * ((offsets[i] >> 6) + 3 i) and is stored twice over: units
+ *                          0 .. (2 n + 143) >> 4 (at least (n >> 4) + 5) hold the bases S[b mod n], so every rotation of the
+ *                          circular record is a linear window (256-bit loads, no wrap logic);
+ *   CK_F_SINGLE_COPY       record i starts at byte 16 * ((offsets[i] >> 6) + 2 i) and is followed by its circular extension
+ *                          only (units 0 .. (n >> 4) + 4): less than half the footprint; meant for batches whose records are
+ *                          all <= 512 bases (the host-buffer entries choose it by themselves for such batches).
+ * class_mask: 0 = any record; else a promise about the batch (bit c set = length/alphabet class c may occur, see
+ * CK_CLASS_*), which skips the launches of absent classes; records outside the promise are reported by ck_dev_check(),
+ * never silently dropped. */
 #define CK_CLASS_2BIT_LE_512 (1u << 0)
 #define CK_CLASS_2BIT_LE_2048 (1u << 1)
 #define CK_CLASS_2BIT_LE_65536 (1u << 2)
@@ -176,7 +182,8 @@ int ck_lmsr_index_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offse
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes /* 0 for the packed2 entry */);
 /* bytes of the CK_F_ALIGNED_OUT arena of a batch (host and device entries) */
 uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records);
-/* flags: CK_F_NO_BYTES, CK_F_ALIGNED_OUT */
+uint64_t ck_packed2_words(uint64_t total_bytes, uint32_t n_records, uint32_t flags /* CK_F_SINGLE_COPY or 0 */);
+/* flags: CK_F_NO_BYTES, CK_F_ALIGNED_OUT, CK_F_SINGLE_COPY */
 int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets,
                          uint32_t n_records, uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start,
                          uint8_t *out_strand, uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
@@ -269,10 +276,10 @@ int ck_synth_offsets(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_in
  * (period 1, 2, 3, 7, 171, n/2) or carry >= 1 kb poly-A runs (config 4) */
 int ck_synth_packed2(ck_ctx *ctx, void *stream, uint64_t seed, uint64_t first_index, uint32_t n_records,
                      const uint64_t *offsets_dev, uint32_t dup_permille, uint32_t adversarial_permille,
-                     uint64_t *packed2_dev);
+                     uint64_t *packed2_dev, uint32_t flags /* CK_F_SINGLE_COPY or 0 */);
 /* 2-bit arena -> ASCII arena (record i at offsets[i]) */
 int ck_dev_unpack2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets, uint32_t n_records,
-                   uint8_t *ascii_out);
+                   uint8_t *ascii_out, uint32_t flags /* CK_F_SINGLE_COPY or 0 */);
 
 #ifdef __cplusplus
 }

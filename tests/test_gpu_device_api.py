@@ -117,6 +117,40 @@ def test_packed_arena_holds_every_record_doubled(env):
             assert int(u) == want, (i, L, j)
 
 
+def test_packed_arena_single_copy_layout(env):
+    """CK_F_SINGLE_COPY (batches of records <= 512 bases): record i at 16-byte granule (offsets[i] >> 6) + 2 i, units
+    0 .. (n >> 4) + 4 hold S[b mod n]; the same records give the same results in either layout."""
+    ctx, D, torch = env
+    n = 400
+    b = D.synth_batch(ctx, seed=5, first_index=0, n_records=n, kind=0, lo=1, hi=512, dup_permille=300)
+    assert b.single
+    ascii_ = D.unpack_ascii(ctx, b, n).cpu().numpy()
+    off = b.offsets.cpu().numpy().astype(np.int64)
+    words = b.packed2.cpu().numpy().view(np.uint32)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    for i in list(range(40)) + [n - 1]:
+        L = int(off[i + 1] - off[i])
+        g = (int(off[i]) >> 6) + 2 * i
+        units = words[4 * g: 4 * g + (L >> 4) + 5]
+        seq = [code[int(c)] for c in ascii_[off[i]: off[i + 1]]]
+        for j, u in enumerate(units):
+            want = 0
+            for k in range(16):
+                want = (want << 2) | seq[(16 * j + k) % L]
+            assert int(u) == want, (i, L, j)
+    b2 = D.synth_batch(ctx, seed=5, first_index=0, n_records=n, kind=0, lo=1, hi=512, dup_permille=300, single=False)
+    assert not b2.single and torch.equal(b.offsets, b2.offsets)
+    res = []
+    for bb in (b, b2):
+        outs = D.CanonOutputs(n, bb.total, bb.offsets.device, want_bytes=True, want_hash=True, aligned=True)
+        outs.out.zero_()
+        ws = D.Workspace(ctx, n)
+        D.canon_packed2(ctx, bb, outs, ws)
+        D.check(ctx, ws)
+        res.append(outs)
+    assert torch.equal(res[0].hash, res[1].hash) and torch.equal(res[0].start, res[1].start) and torch.equal(res[0].strand, res[1].strand)
+
+
 def test_class_promise_violation_is_reported(env):
     import circkit_b200
     ctx, D, torch = env

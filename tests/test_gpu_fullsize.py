@@ -71,9 +71,9 @@ def _unique_fraction(ctx, D, torch, outs, n):
 
 
 @pytest.mark.parametrize("name,n,kind,lo,hi,dup,adv,seed,prefix", [
-    ("config 2: 10 M circRNA-length records, 30 % duplicates", 10_000_000, 1, 200, 5000, 300, 0, 2, 4000),
-    ("config 5 shard: 12.5 M viroid-length records, 30 % duplicates", 12_500_000, 0, 250, 400, 300, 0, 5, 20000),
-    ("config 4: 200 k plasmid-length records, 1 % adversarial", 200_000, 1, 5000, 200_000, 0, 10, 4, 40),
+    ("config 2: 10 M circRNA-length records, 30 % duplicates", 10_000_000, 1, 200, 5000, 300, 0, 2, 100_000),
+    ("config 5 shard: 12.5 M viroid-length records, 30 % duplicates", 12_500_000, 0, 250, 400, 300, 0, 5, 100_000),
+    ("config 4: 200 k plasmid-length records, 1 % adversarial", 200_000, 1, 5000, 200_000, 0, 10, 4, 3000),
 ])
 def test_full_size_two_bit_configs(env, name, n, kind, lo, hi, dup, adv, seed, prefix):
     ctx, D, torch = env
