@@ -879,7 +879,7 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
     from circkit_b200.device import CLASS_NAMES
     # (the small per-class launches run side by side on forked streams: the interval of a launch with no records can be as
     # long as the kernel it waited behind, so only classes that hold records of this batch are candidates)
-    byte_ranges = {"4bit_le_2048": (1, 2048), "4bit_le_212992": (2049, 212992), "byte_le_1024": (1, 1024), "byte_le_106496": (1025, 106496)}
+    byte_ranges = {"4bit_lane_129_2048": (129, 2048), "4bit_le_2048": (1, 2048), "4bit_le_212992": (2049, 212992), "byte_le_1024": (1, 1024), "byte_le_106496": (1025, 106496)}
 
     def holds_records(c):
         lo_c, hi_c = D.CLASS_RANGE.get(c) or byte_ranges.get(c, (0, 0))
@@ -912,7 +912,7 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
         except Exception:
             traffic = None
     kernel_share = {c: round(ktimes[c][0] / steps, 4) for c in CLASS_NAMES if ktimes[c][1]}
-    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_seg (warp per record, a lane per segment, 16-mer keys)" if "seg" in dom else "k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s3 (lane per record, streaming, 256-bit loads)", dom),
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % ("k_canon_seg (warp per record, a lane per segment, 16-mer keys)" if "seg" in dom else "k_canon_cta<2>" if "65536" in dom or "425984" in dom else "k_canon_l4 (lane per record, 4-bit strands packed by k_pack4)" if dom.startswith("4bit_lane") else "k_canon_warp (byte-level lane)" if byte_lane else "k_canon_s2 (lane per record, single-copy arena, 128-bit loads)" if getattr(batch, "single", False) else "k_canon_s3 (lane per record, doubled arena, 256-bit loads)", dom),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes / launches_per_step),

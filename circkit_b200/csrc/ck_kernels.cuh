@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
             else if (bits == 2) cls = n <= cls_max_n(CLS_W2S) ? CLS_W2S : n <= cls_max_n(CLS_W2M) ? CLS_W2M
                                     : n <= cls_max_n(CLS_W2L) ? CLS_W2L : n <= cls_max_n(CLS_W2X) ? CLS_W2X
                                     : n <= cls_max_n(CLS_C2A) ? CLS_C2A : n <= cls_max_n(CLS_C2B) ? CLS_C2B : CLS_HUGE;
-            else if (bits == 4) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
+            else if (bits == 4 || bits == 3) cls = n <= cls_max_n(CLS_W4) ? CLS_W4 : n <= cls_max_n(CLS_C4) ? CLS_C4 : CLS_HUGE;
             else cls = n <= cls_max_n(CLS_W8) ? CLS_W8 : n <= cls_max_n(CLS_C8) ? CLS_C8 : CLS_HUGE;
         }
         if (a.direct_mask) {

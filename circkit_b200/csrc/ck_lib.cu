@@ -21,6 +21,7 @@
 #include "ck_stream2.cuh"
 #include "ck_stream3.cuh"
 #include "ck_seg2.cuh"
+#include "ck_lane4.cuh"
 #include "ck_synth.cuh"
 #include "ck_monomerize.cuh"
 
@@ -88,7 +89,7 @@ struct ExecScratch {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t inserted = nullptr;     // recorded after this slot's table insert
-    u8 *d_raw = nullptr; u64 *d_off = nullptr; u64 *d_p2 = nullptr; u8 *d_norm = nullptr;
+    u8 *d_raw = nullptr; u64 *d_off = nullptr; u64 *d_p2 = nullptr; u8 *d_norm = nullptr; u8 *d_p4 = nullptr;
     u32 *d_len = nullptr; u8 *d_lane = nullptr; u8 *d_out = nullptr; u32 *d_start = nullptr;
     u8 *d_strand = nullptr; u64 *d_hash = nullptr; u64 *d_first = nullptr; u64 *d_slotof = nullptr;
     u32 *d_lists = nullptr; u32 *d_counts = nullptr;
@@ -136,11 +137,12 @@ struct ck_ctx {
     u64 launches = 0;
     bool attrs_set = false;
     u32 s3_debug = 0;                   // CK_S3_DEBUG: bits 8.. switch the lane kernel's L2 prefetches off (traffic experiments)
+    bool l4_kernel = true;              // CK_L4_KERNEL=0: {-ACGNT} records go to the generic 4-bit kernels only (A/B runs)
     bool seg_kernel = true;             // CK_SEG_KERNEL=0: long 2-bit records go to the CTA kernels only (A/B runs)
     int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
-    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 4];     // [CLS_COUNT] = lane kernel, table insert, table first, [CLS_COUNT + 3] = segment kernel
+    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 6];     // [CLS_COUNT] = lane kernel, table insert, table first, segment kernel, 4-bit lane kernel, k_pack4
 };
 
 namespace {
@@ -265,6 +267,9 @@ int set_attrs(ck_ctx *ctx)
     if ((rc = set_smem(ctx, k_canon_s3<0>, s3)) || (rc = set_smem(ctx, k_canon_s3<1>, s3)) || (rc = set_smem(ctx, k_canon_s3<2>, s3)) ||
         (rc = set_smem(ctx, k_canon_s3<3>, s3)) || (rc = set_smem(ctx, k_canon_s3<4>, s3)) || (rc = set_smem(ctx, k_canon_s3<5>, s3)) ||
         (rc = set_smem(ctx, k_canon_s3<6>, s3)) || (rc = set_smem(ctx, k_canon_s3<7>, s3))) return rc;
+    const u32 l4 = CK_L4_WARPS * CK_L4_WARP_BYTES;
+    if ((rc = set_smem(ctx, k_canon_l4<0>, l4)) || (rc = set_smem(ctx, k_canon_l4<1>, l4)) || (rc = set_smem(ctx, k_canon_l4<2>, l4)) ||
+        (rc = set_smem(ctx, k_canon_l4<3>, l4))) return rc;
     ctx->attrs_set = true;
     return CK_OK;
 }
@@ -273,6 +278,7 @@ struct CanonIO {
     const u64 *packed2; const u8 *bytes; const u64 *offsets; const u32 *lens; const u8 *lane;
     u32 n; u32 mode;
     u32 dbl = 1;                      // packed2 layout of the batch: 1 doubled (ck_stream3 / ck_seg2), 0 single copy (ck_stream2)
+    u8 *p4 = nullptr;                 // optional packed4 arena (ck_lane4.cuh), p4_bytes_total(total, n) bytes: enables k_canon_l4
     u8 *out; u32 *out_start; u8 *out_strand; u64 *out_hash;
     u32 *lists; u64 lists_bytes;      // sort workspace: >= ck_lists_bytes(n)
     u32 *counts;                      // 32 u32: class counts, run starts
@@ -306,6 +312,16 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         u32 wbits = 0;
         while ((((u64)io.n - 1) >> window_shift) >> wbits) wbits++;
         top_bit = std::max(14u, 5u + wbits);
+    }
+    // records over {-, A, C, G, N, T} (what needletail's normalisation leaves of IUPAC input): both strands packed at 4 bits
+    // for the lane-per-record kernel of ck_lane4.cuh; their lane tag becomes 3
+    const bool l4_run = fastv && only < 0 && ctx->l4_kernel && io.p4 && io.lane && io.bytes && (!class_mask || (class_mask & (1u << CLS_W4)));
+    if (l4_run) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->timing) { CK_CUDA(ctx, cudaEventCreate(&e0)); CK_CUDA(ctx, cudaEventCreate(&e1)); CK_CUDA(ctx, cudaEventRecord(e0, st)); }
+        k_pack4<<<std::min<u32>((io.n + 7) / 8, 16u * (u32)ctx->num_sms), 256, 0, st>>>(io.bytes, io.offsets, io.lens, const_cast<u8 *>(io.lane), io.n, io.p4);
+        if (ctx->timing) { CK_CUDA(ctx, cudaEventRecord(e1, st)); ctx->ev_pairs[CLS_COUNT + 5].push_back(e0); ctx->ev_pairs[CLS_COUNT + 5].push_back(e1); }
+        ctx->launches++;
     }
     const int sort_bits = (int)top_bit + 1;
     ClassifyArgs ca{io.offsets, io.lens, io.lane, io.n, k0, v0, io.counts, only >= 0 ? (1u << only) : 0u, window_shift, top_bit};
@@ -379,6 +395,21 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         CK_CUDA(ctx, timed(CLS_COUNT + 3, e0, e1, false, st));
         ctx->launches++;
     }
+    if (l4_run) {
+        CanonArgs a = base_args(CLS_W4);
+        a.list = sorted; a.count = io.counts + CLS_W4; a.n_direct = 0;
+        const u32 g = 2u * (u32)ctx->num_sms, th = 32u * CK_L4_WARPS, sm = CK_L4_WARPS * CK_L4_WARP_BYTES;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        CK_CUDA(ctx, timed(CLS_COUNT + 4, e0, e1, true, st));
+        switch ((a.out_hash ? CK_W2_HASH : 0) | (a.out ? CK_W2_OUT : 0)) {
+        case 0: k_canon_l4<0><<<g, th, sm, st>>>(a, io.p4, io.lane); break;
+        case 1: k_canon_l4<1><<<g, th, sm, st>>>(a, io.p4, io.lane); break;
+        case 2: k_canon_l4<2><<<g, th, sm, st>>>(a, io.p4, io.lane); break;
+        default: k_canon_l4<3><<<g, th, sm, st>>>(a, io.p4, io.lane); break;
+        }
+        CK_CUDA(ctx, timed(CLS_COUNT + 4, e0, e1, false, st));
+        ctx->launches++;
+    }
     u32 to_launch = 0;
     for (int c = 0; c < CLS_COUNT; c++)
         if (c != CLS_HUGE && !(class_mask && !(class_mask & (1u << c)))) to_launch++;
@@ -390,7 +421,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         if (class_mask && !(class_mask & (1u << c))) continue;
         CanonArgs a = base_args(c);
         const bool is_lane_cls = ((lane_classes >> c) & 1u) != 0;
-        if ((lane_run && is_lane_cls) || (seg_run && ((seg_classes >> c) & 1u))) { a.list = retry; a.count = io.counts + 32 + c; a.n_direct = 0; }   // what the lane / segment kernel left over
+        if ((lane_run && is_lane_cls) || (seg_run && ((seg_classes >> c) & 1u)) || (l4_run && c == CLS_W4)) { a.list = retry; a.count = io.counts + 32 + c; a.n_direct = 0; }   // what the lane / segment kernel left over
         else if (only >= 0) { a.list = nullptr; a.count = nullptr; a.n_direct = io.n; }
         else { a.list = sorted; a.count = io.counts + c; a.n_direct = 0; }
         const u32 grid = kCls[c].ctas_per_sm * (u32)ctx->num_sms, thr = kCls[c].threads;
@@ -568,7 +599,7 @@ int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
     CanonIO io{};
     // without normalisation every byte is a symbol: lengths are the offset differences and the lane-per-record kernel applies
     io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = lens_given ? s.d_len : nullptr; io.lane = s.d_lane;
-    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u; io.dbl = s.dbl;
+    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u; io.dbl = s.dbl; io.p4 = s.d_p4;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
@@ -723,6 +754,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     ctx->device = cfg->device;
     if (const char *dbg = getenv("CK_S3_DEBUG")) ctx->s3_debug = (u32)strtoul(dbg, nullptr, 0) & 0xff00u;
     if (const char *sk = getenv("CK_SEG_KERNEL")) ctx->seg_kernel = atoi(sk) != 0;
+    if (const char *lk = getenv("CK_L4_KERNEL")) ctx->l4_kernel = atoi(lk) != 0;
     if (const char *lk = getenv("CK_LANE_KERNEL")) ctx->lane_kernel = atoi(lk) == 2 ? 2 : 3;
 #define CK_INIT(call)                                                                          \
     do {                                                                                       \
@@ -759,6 +791,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
             CK_INIT(cudaMalloc(&s.d_norm, B + 16));
             CK_INIT(cudaMalloc(&s.d_out, out_bytes_total(B, R) + 64));
             CK_INIT(cudaMalloc(&s.d_p2, p2_words(B, R) * 8));
+            CK_INIT(cudaMalloc(&s.d_p4, p4_bytes_total(B, R)));
             CK_INIT(cudaMalloc(&s.d_off, (R + 1) * 8));
             CK_INIT(cudaMalloc(&s.d_len, (R + 1) * 4));
             CK_INIT(cudaMalloc(&s.d_lane, R + 1));
@@ -799,7 +832,7 @@ void ck_destroy(ck_ctx *ctx)
     for (int k = 0; k < 2; k++) {
         Slot &s = ctx->slot[k];
         void *ptrs[] = {s.d_raw, s.d_off, s.d_p2, s.d_norm, s.d_len, s.d_lane, s.d_out, s.d_start, s.d_strand,
-                        s.d_hash, s.d_first, s.d_slotof, s.d_lists, s.d_counts, s.d_dense, s.d_laneoff};
+                        s.d_hash, s.d_first, s.d_slotof, s.d_lists, s.d_counts, s.d_dense, s.d_laneoff, s.d_p4};
         for (void *p : ptrs) if (p) cudaFree(p);
         if (s.h_counts) cudaFreeHost(s.h_counts);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -1095,7 +1128,7 @@ int ck_canonicalize(ck_ctx *ctx, const uint8_t *s, size_t n, uint8_t *out)
 uint64_t ck_dev_workspace_bytes(uint32_t n_records, uint64_t total_bytes)
 {
     u64 b = 256 + lists_bytes_for(n_records);
-    if (total_bytes) b += p2_words(total_bytes, n_records) * 8 + total_bytes + 64 + 5ull * (n_records + 16);
+    if (total_bytes) b += p2_words(total_bytes, n_records) * 8 + total_bytes + 64 + ((5ull * (n_records + 16) + 63) & ~63ull) + p4_bytes_total(total_bytes, n_records);
     return (b + 255) & ~255ull;
 }
 uint64_t ck_out_arena_bytes(uint64_t total_bytes, uint32_t n_records) { return out_bytes_total(total_bytes, n_records); }
@@ -1137,14 +1170,15 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     u32 *lists = (u32 *)w; w += lists_bytes_for(n_records);
     u64 *p2 = (u64 *)w; w += p2_words(total_bytes, n_records) * 8;
     u8 *norm = w; w += (total_bytes + 63) & ~63ull;
-    u8 *lane = w;
+    u8 *lane = w; w += ((size_t)n_records + 63) & ~63ull;
+    u8 *p4 = w;
     cudaStream_t st = (cudaStream_t)stream;
     PrepareArgs pa{bytes, U(offsets), n_records, (flags & CK_F_NORMALIZE) | (1u << 2), p2, norm, out_len, lane};
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
     k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records, nullptr, 1u);
     ctx->launches += 2;
     CanonIO io{};
-    io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records;
+    io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records; io.p4 = p4;
     io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : out_bytes; io.out_start = out_start; io.out_strand = out_strand;
     io.out_hash = U(out_hash64); io.counts = counts; io.lists = lists; io.lists_bytes = lists_bytes_for(n_records);
@@ -1325,7 +1359,7 @@ int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_
     if (!ctx || !out_ms || !out_launches) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     CK_CUDA(ctx, cudaDeviceSynchronize());
     for (u32 c = 0; c < n_classes; c++) { out_ms[c] = 0; out_launches[c] = 0; }
-    for (u32 c = 0; c < (u32)CLS_COUNT + 4; c++) {
+    for (u32 c = 0; c < (u32)CLS_COUNT + 6; c++) {
         std::vector<cudaEvent_t> &v = ctx->ev_pairs[c];
         for (size_t k = 0; k + 1 < v.size(); k += 2) {
             float ms = 0;

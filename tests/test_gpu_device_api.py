@@ -315,3 +315,68 @@ def test_padded_owner_partition(env, world):
     pairs2, pos2, state2 = part.padded(h2, base, world)
     assert int(state2[world]) == 1 and int(state2[0]) == n
     assert int((pos2.long() == 0xffffffff).sum() + (pos2 == -1).sum()) == n - cap
+
+
+@pytest.mark.parametrize("want_bytes,want_hash", [(True, True), (True, False), (False, True), (False, False)])
+def test_cli_alphabet_lane_kernel(env, want_bytes, want_hash):
+    """ck_lane4.cuh: records over {-, A, C, G, N, T} after needletail's normalisation (src/canonicalize.rs:24-27; config 3 of
+    BASELINE.json) -- every length around the oct (64-symbol) edges, the 129 / 241 fast-path limits and the 2048 class limit,
+    random, IUPAC (normalised to N), and every tie shape (periodic, dimers, reverse-palindromic circles, N runs), all four
+    kernel variants, start / strand / bytes / XXH3 against the oracle."""
+    ctx, D, torch = env
+    import random
+    rng = random.Random(4 + 2 * want_bytes + want_hash)
+    alpha = b"ACGTN-"
+
+    def rnd(n, al=alpha):
+        return bytes(rng.choice(al) for _ in range(n))
+    seqs = []
+    for n in list(range(120, 330)) + list(range(380, 390)) + [447, 448, 449, 511, 512, 513, 1000, 1023, 1024, 1025, 1984, 2047, 2048, 2049, 2100]:
+        seqs.append(rnd(n))
+        seqs.append(rnd(n, b"ACGTNRYKMSWBDHVacgtnu"))                   # normalised: IUPAC -> N
+        k = rng.randrange(6)
+        if k == 0:
+            u = rnd(rng.randint(1, 40)); seqs.append((u * (n // len(u) + 1))[:n])           # near-periodic (cut power)
+        elif k == 1:
+            h = rnd(n // 2); seqs.append(h + h)                                             # dimer
+        elif k == 2:
+            h = rnd(n // 2); seqs.append(h + oracle.revcomp(h))                             # reverse-palindromic circle
+        elif k == 3:
+            s = bytearray(rnd(n)); a = rng.randrange(n)
+            for j in range(rng.randint(8, n)):
+                s[(a + j) % n] = ord("-")                                                   # long run of the smallest symbol
+            seqs.append(bytes(s))
+        elif k == 4:
+            seqs.append(b"N" * n)
+        else:
+            s = bytearray(rnd(n, b"ACGT")); s[rng.randrange(n)] = ord("N"); seqs.append(bytes(s))   # a single N
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64); np.cumsum(lens, out=off[1:])
+    arena = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    n, total = len(seqs), int(off[-1])
+    dev = torch.device("cuda", ctx.device)
+    raw = torch.from_numpy(arena.copy()).to(dev)
+    offsets = torch.from_numpy(off).to(dev)
+    ws = D.Workspace(ctx, n, total)
+    outs = D.CanonOutputs(n, total, dev, want_bytes=want_bytes, want_hash=want_hash, aligned=True)
+    lens_out = torch.empty(n, dtype=torch.int32, device=dev)
+    ctx._lib.ck_kernel_timing(ctx.handle, 1)
+    D.kernel_times(ctx)
+    D.canon_bytes(ctx, raw, offsets, n, total, outs, lens_out, ws, normalize=True)
+    D.check(ctx, ws)
+    times = D.kernel_times(ctx)
+    ctx._lib.ck_kernel_timing(ctx.handle, 0)
+    assert times["4bit_lane_129_2048"][1] == 1 and times["pack4"][1] == 1, times      # the kernel under test did run
+    want = oracle.canonicalize_batch(arena, off.astype(np.uint64), normalize=True, threads=8)
+    assert np.array_equal(lens_out.cpu().numpy().astype(np.int64), want["lens"].astype(np.int64))
+    bad = np.flatnonzero((outs.start.cpu().numpy().astype(np.int64) != want["start"].astype(np.int64))
+                         | (outs.strand.cpu().numpy() != want["strand"]))
+    assert bad.size == 0, (bad[:5], [seqs[i][:50] for i in bad[:3]])
+    if want_hash:
+        assert np.array_equal(outs.hash.cpu().numpy().astype(np.uint64), want["hash"])
+    if want_bytes:
+        out = outs.out.cpu().numpy()
+        starts = 32 * ((off[:-1] >> 5) + np.arange(n))
+        for i in range(n):
+            a, ln = int(off[i]), int(lens[i])
+            assert out[starts[i]: starts[i] + ln].tobytes() == want["out"][a: a + ln].tobytes(), (i, ln, seqs[i][:60])
