@@ -56,10 +56,12 @@ def parse_args():
                          "PCIe (~55 GB/s) work side by side instead of one after the other; 0 = every batch packed on the host")
     ap.add_argument("--no-config5", action="store_true", help="default workload only: skip the 100 M-record config-5 sub-record")
     ap.add_argument("--c5-records", type=int, default=100_000_000, help="records of the config-5 sub-record, split over the GPUs")
-    ap.add_argument("--overlap", action="store_true",
+    ap.add_argument("--overlap", dest="overlap", action="store_true", default=None,
                     help="uniq: run the table / exchange stage of a step on a second stream with double-buffered outputs, so that "
-                         "it overlaps the canonicalisation of the next step (measured: +3-7 % on config 2, but the table's random "
-                         "atomics can halve the speed of the latency-bound lane kernel on config 5, so it is off by default)")
+                         "it overlaps the canonicalisation of the next step.  Default: on with more than one GPU (round 2, 2 GPUs: "
+                         "config 2 +3.4 %%, config 5 +6-7 %%), off on one GPU (+1 %%, and the kernel timings of the roofline then "
+                         "include the table's traffic)")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false")
     ap.add_argument("--exchange", default="peer", choices=["peer", "symm", "padded", "exact"],
                     help="multi-GPU uniq, how (hash, index) pairs reach their owner: peer = stored straight into the owner's buffer by "
                          "the partition kernel over NVLink (fixed-capacity buckets, device-side barriers, no collective); padded = "
@@ -747,9 +749,11 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
             config["sharding"] += " [symmetric memory unavailable on this node (%s): fixed-capacity buckets through NCCL instead]" % (why or "another rank")
     stage_stream, outs_sets, first_sets, pipe, partitioner = None, None, None, None, None
     if w["uniq"] and raw_dev is None:
-        overlap = args.overlap and world > 1
+        overlap = args.overlap if args.overlap is not None else world > 1
         slots_1gpu = torch.empty(max(R, 1), dtype=torch.int64, device=dev) if world == 1 else None
         stage_stream = torch.cuda.Stream(device=dev) if overlap else None
+        config["pipelining"] = ("table / exchange stage of step k on a second stream, overlapping the kernels of step k + 1 (double-buffered outputs)"
+                                if overlap else "none: every step's stages in stream order")
         outs_sets = [outs, D.CanonOutputs(R, batch.total, dev, want_bytes=True, want_hash=True, aligned=True) if overlap else outs]
         first_sets = [first, torch.empty_like(first) if overlap else first]
         pipe = dict(k=0, done=[torch.cuda.Event(), torch.cuda.Event()], canon=[torch.cuda.Event(), torch.cuda.Event()])
@@ -768,7 +772,7 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
         pipe["k"] += 1
         o_i, f_i = outs_sets[i], first_sets[i]
         cur = torch.cuda.current_stream()
-        if world == 1:
+        if world == 1 and stage_stream is None:
             # one GPU: canonicalise + hash, then the table passes, straight into this step's result buffer
             D.canon_packed2(ctx, batch, o_i, ws, class_mask=w["mask"])
             table.clear()
@@ -782,7 +786,10 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
         with torch.cuda.stream(st):
             st.wait_event(pipe["canon"][i])
             table.clear()
-            if peer_group is not None:              # exact counts, no padding, nothing to check afterwards
+            if world == 1:
+                table.insert(o_i.hash[:R], R, slots_1gpu, base_index=base_index)
+                table.first(slots_1gpu, R, f_i)
+            elif peer_group is not None:            # exact counts, no padding, nothing to check afterwards
                 peer_group.first_index(o_i.hash[:R], base_index, table, f_i)
             elif padded["on"]:
                 # fixed-capacity buckets: no counts to exchange, no host synchronisation in the step; an overflowing bucket is
