@@ -150,7 +150,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
 {
     const u64 off = a.offsets[rec];
     const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
-    if ((a.list == nullptr || (a.mode & 0x200u)) && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform); 0x200: a tier of a list
+    if (a.list == nullptr && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform)
     RecordIn in;
     in.packed2 = a.packed2 ? a.packed2 + p2_word(off, rec, a.p2_dbl) : nullptr;
     in.bytes = a.bytes ? a.bytes + off : nullptr;

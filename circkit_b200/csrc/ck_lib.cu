@@ -137,7 +137,6 @@ struct ck_ctx {
     u64 launches = 0;
     bool attrs_set = false;
     u32 s3_debug = 0;                   // CK_S3_DEBUG: bits 8.. switch the lane kernel's L2 prefetches off (traffic experiments)
-    bool c2b_tiers = true;              // CK_C2B_TIERS=0: one launch of 1024-thread CTAs for the longest 2-bit retry class
     bool l4_kernel = true;              // CK_L4_KERNEL=0: {-ACGNT} records go to the generic 4-bit kernels only (A/B runs)
     bool seg_kernel = true;             // CK_SEG_KERNEL=0: long 2-bit records go to the CTA kernels only (A/B runs)
     int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
@@ -208,7 +207,7 @@ int alloc_scratch(ck_ctx *ctx, ExecScratch &s)
     for (int c = 0; c < CLS_COUNT; c++) {
         if (kCls[c].bits == 0) continue;
         const u64 groups = (u64)kCls[c].ctas_per_sm * ctx->num_sms * (kCls[c].cta ? 1u : kCls[c].threads / 32u);
-        CK_CUDA(ctx, cudaMalloc(&s.tie[c], (groups + (c == CLS_C2B ? 8 : 0)) * cls_tie_words(c) * 4));    // C2B: two half-size tiers side by side
+        CK_CUDA(ctx, cudaMalloc(&s.tie[c], groups * cls_tie_words(c) * 4));
     }
     return CK_OK;
 }
@@ -439,20 +438,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
         switch (c) {
         case CLS_W2S: k_canon_w2<true, -1><<<grid, thr, smem, sc>>>(a); break;
         case CLS_W2M: case CLS_W2L: case CLS_W2X: k_canon_w2<false, -1><<<grid, thr, smem, sc>>>(a); break;
-        case CLS_C2A: k_canon_cta<2, false><<<grid, thr, smem, sc>>>(a); break;
-        case CLS_C2B:
-            if (seg_run && ctx->c2b_tiers) {
-                // what the segment kernel left of this class (repeats): a CTA of 1024 threads with the whole 213 KB of shared memory
-                // per record keeps the ALU pipe 20 % busy; records up to 212 992 bases -- all but the very longest -- take half of
-                // it, so two CTAs of 512 threads walk the list side by side per SM, each taking the entries of its tier
-                CanonArgs lo = a, hi = a;
-                lo.mode |= 0x200u; lo.max_n = 212992u; lo.smem_units = strand_units<2>(lo.max_n); lo.scratch_stride = tie_scratch_words<2>(lo.max_n);
-                hi.mode |= 0x200u; hi.min_n = lo.max_n + 1;
-                k_canon_cta<2, false><<<2 * grid, 512, 2u * lo.smem_units * 4u, sc>>>(lo);
-                k_canon_cta<2, false><<<grid, thr, smem, sc>>>(hi);
-                ctx->launches++;
-            } else k_canon_cta<2, false><<<grid, thr, smem, sc>>>(a);
-            break;
+        case CLS_C2A: case CLS_C2B: k_canon_cta<2, false><<<grid, thr, smem, sc>>>(a); break;
         case CLS_W4: k_canon_warp<4><<<grid, thr, smem, sc>>>(a); break;
         case CLS_C4: k_canon_cta<4, false><<<grid, thr, smem, sc>>>(a); break;
         case CLS_W8: k_canon_warp<8><<<grid, thr, smem, sc>>>(a); break;
@@ -769,7 +755,6 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     if (const char *dbg = getenv("CK_S3_DEBUG")) ctx->s3_debug = (u32)strtoul(dbg, nullptr, 0) & 0xff00u;
     if (const char *sk = getenv("CK_SEG_KERNEL")) ctx->seg_kernel = atoi(sk) != 0;
     if (const char *lk = getenv("CK_L4_KERNEL")) ctx->l4_kernel = atoi(lk) != 0;
-    if (const char *tk = getenv("CK_C2B_TIERS")) ctx->c2b_tiers = atoi(tk) != 0;
     if (const char *lk = getenv("CK_LANE_KERNEL")) ctx->lane_kernel = atoi(lk) == 2 ? 2 : 3;
 #define CK_INIT(call)                                                                          \
     do {                                                                                       \

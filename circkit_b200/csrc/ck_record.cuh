@@ -168,6 +168,35 @@ template <int BITS> __device__ __forceinline__ u32 duel(const u32 *X, u32 n, u32
     return a;
 }
 
+// The same duel by a whole warp (all lanes call it with the same a, b): lane l compares symbols [off + l S, off + (l + 1) S),
+// the first lane that sees a difference decides.  The late rounds of the tournament have few pairs that lie far apart --
+// in a periodic record they agree on all of the b - a symbols between them -- and one thread walking 16 symbols per step
+// (while the rest of the group waits at the barrier) was 70 % of the CTA kernel's time on config 4's repeats.
+template <int BITS> __device__ __forceinline__ u32 duel_warp(const u32 *X, u32 n, u32 a, u32 b)
+{
+    constexpr int S = Lane<BITS>::S;
+    const u32 d = b - a, lane = threadIdx.x & 31u;
+    for (u32 off0 = 0; off0 < d; off0 += 32u * S) {
+        const u32 off = off0 + lane * S;
+        u32 wa = 0, wb = 0;
+        if (off < d) {
+            u32 pa = a + off, pb = b + off;                 // a, b < n and off < d < n: one wrap at most
+            if (pa >= n) pa -= n;
+            if (pb >= n) pb -= n;
+            wa = window32<BITS>(X, pa); wb = window32<BITS>(X, pb);
+        }
+        const u32 m = __ballot_sync(CK_FULL, wa != wb);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            const u32 wal = __shfl_sync(CK_FULL, wa, l), wbl = __shfl_sync(CK_FULL, wb, l);
+            const u32 ds = __clz(wal ^ wbl) / BITS;
+            if (off0 + (u32)l * S + ds < d) return wal < wbl ? a : b;
+            return a;                                       // agree on the first d symbols
+        }
+    }
+    return a;
+}
+
 // Reduce the tied candidates of one strand to a single survivor.  Returns 0xffffffff if none.
 // scr layout: bitmap[(n+31)/32] | listA[cap] | listB[cap]
 template <int BITS, typename G>
@@ -221,7 +250,13 @@ __device__ u32 strand_tie_winner(const u32 *X, u32 n, typename KeyOf<BITS>::type
     u32 *src = listA, *dst = listB;
     while (m > 1) {
         u32 pairs = m >> 1;
-        for (u32 t = rank; t < pairs; t += gs) dst[t] = duel<BITS>(X, n, src[2 * t], src[2 * t + 1]);
+        if (pairs <= (gs >> 4)) {                           // at most two pairs per warp: a warp per pair
+            for (u32 t = rank >> 5; t < pairs; t += gs >> 5) {
+                const u32 w = duel_warp<BITS>(X, n, src[2 * t], src[2 * t + 1]);
+                if ((rank & 31u) == 0) dst[t] = w;
+            }
+        } else
+            for (u32 t = rank; t < pairs; t += gs) dst[t] = duel<BITS>(X, n, src[2 * t], src[2 * t + 1]);
         if ((m & 1u) && rank == 0) dst[pairs] = src[m - 1];
         G::sync();
         m = pairs + (m & 1u);
