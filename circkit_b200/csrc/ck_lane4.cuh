@@ -52,37 +52,58 @@ __device__ __forceinline__ u32 l4_nibrev(u32 x)
     const u32 r = __byte_perm(x, 0, 0x0123);
     return ((r & 0x0f0f0f0fu) << 4) | ((r >> 4) & 0x0f0f0f0fu);
 }
-// the 8 symbols of the circle that start at symbol q (< n) of a first copy X (units zero-padded past n, X[units] = 0)
-__device__ __forceinline__ u32 l4_win(const u32 *X, u32 n, u32 q)
+// the 8 symbols of the circle that start at symbol q (< n) of a first copy X that l4_close() has continued past n
+__device__ __forceinline__ u32 l4_win(const u32 *X, u32 q)
 {
     const u32 k = q >> 3;
-    u32 a = __funnelshift_l(X[k + 1], X[k], 4u * (q & 7u));
-    const u32 v = n - q;
-    if (v < 8u) a = (a & ~(0xffffffffu >> (4u * v))) | (X[0] >> (4u * v));
-    return a;
+    return __funnelshift_l(X[k + 1], X[k], 4u * (q & 7u));
+}
+// continue a zero-padded first copy (NU units, n symbols) circularly: the free nibbles of its last unit and two more units
+__device__ __forceinline__ void l4_close(u32 *X, u32 n, u32 NU)
+{
+    const u32 v = n - 8u * (NU - 1u), f0 = X[0], f1 = X[1];          // 1..8 symbols in the last unit
+    if (v < 8u) {
+        const u32 s = 4u * (8u - v);
+        X[NU - 1u] |= f0 >> (4u * v);
+        X[NU] = __funnelshift_l(f1, f0, s);
+        X[NU + 1u] = __funnelshift_l(X[2], f1, s);
+    } else { X[NU] = f0; X[NU + 1u] = f1; }
 }
 
-// one warp per record of the 4-bit lane with 129 <= n <= 2048: both strands, doubled; lane_bits[i] becomes 3.
-//   A: 8 bytes per lane -> one unit of the forward first copy (shared memory), alphabet check;
+// Half a warp per record of the 4-bit lane with 129 <= n <= 2048 (a 325-symbol record has 41 units: 16 lanes use 85 % of
+// their iterations, 32 lanes 64 %): both strands, doubled; lane_bits[i] becomes 3.
+//   A: 8 bytes per lane -> one unit of the forward first copy (shared memory, then continued circularly by two units so that
+//      every window of the circle is one funnel shift), alphabet check;
 //   B: the reverse complement's first copy from it (window of the forward copy, nibbles reversed, complemented);
-//   C: units of the doubled strands = windows of the first copies at 8 j mod n, 128-byte coalesced stores.
+//   C: units of the doubled strands = windows of the first copies at 8 j mod n, 64-byte coalesced stores.
 #define CK_P4_UNITS 260u
 __global__ void __launch_bounds__(256) k_pack4(const u8 *bytes, const u64 *offsets, const u32 *lens, u8 *lane_bits, u32 n_records, u8 *p4)
 {
-    __shared__ u32 sh[8][2][CK_P4_UNITS];
-    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
-    u32 *F = sh[wid][0], *R = sh[wid][1];
+    __shared__ u32 sh[16][2][CK_P4_UNITS];
+    const u32 lane = lane_id(), hl = lane & 15u, half = lane >> 4;
+    const u32 hmask = half ? 0xffff0000u : 0x0000ffffu;
+    u32 *F = sh[threadIdx.x >> 4][0], *R = sh[threadIdx.x >> 4][1];
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (u32 i = gw; i < n_records; i += nw) {
-        if (lane_bits[i] != 4) continue;
-        const u64 off = offsets[i];
-        const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
-        if (n < 129u || n > 2048u) continue;
+    // the next pair's tag / offset / length are requested, and its bytes prefetched into L2, while this pair is packed
+    u32 nx_i = 2u * gw + half;
+    bool nx_act = nx_i < n_records && lane_bits[nx_i] == 4;
+    u64 nx_off = nx_act ? offsets[nx_i] : 0;
+    u32 nx_n = nx_act ? (lens ? lens[nx_i] : (u32)(offsets[nx_i + 1] - nx_off)) : 0u;
+    for (u32 i0 = 2u * gw; i0 < n_records; i0 += 2u * nw) {
+        const u32 i = nx_i;
+        const u64 off = nx_off;
+        const u32 n = nx_n;
+        bool act = nx_act && n >= 129u && n <= 2048u;
+        nx_i = i0 + 2u * nw + half;
+        nx_act = nx_i < n_records && lane_bits[nx_i] == 4;
+        nx_off = nx_act ? offsets[nx_i] : 0;
+        nx_n = nx_act ? (lens ? lens[nx_i] : (u32)(offsets[nx_i + 1] - nx_off)) : 0u;
+        if (nx_act && 128u * hl < nx_n + 127u && nx_n <= 2048u) prefetch_l2(bytes + (nx_off & ~127ull) + 128u * hl);
         const u32 NU = (n + 7u) >> 3;
         const u32 *w = reinterpret_cast<const u32 *>(bytes + (off & ~3ull));
         const u32 sh8 = 8u * (u32)(off & 3u);
         u32 bad = 0;
-        for (u32 j = lane; j < NU + 2u; j += 32) {
+        for (u32 j = hl; j < (act ? NU + 2u : 0u); j += 16) {
             u32 u = 0;
             if (j < NU) {
                 const u32 w0 = __ldg(w + 2 * j), w1 = __ldg(w + 2 * j + 1), w2 = __ldg(w + 2 * j + 2);
@@ -96,29 +117,33 @@ __global__ void __launch_bounds__(256) k_pack4(const u8 *bytes, const u64 *offse
             F[j] = u;
         }
         __syncwarp();
-        if (__any_sync(CK_FULL, bad != 0)) { __syncwarp(); continue; }     // another alphabet: the generic byte-lane kernels take it
-        for (u32 j = lane; j < NU + 2u; j += 32) {
+        if (__ballot_sync(CK_FULL, bad != 0) & hmask) act = false;         // another alphabet: the generic byte-lane kernels take it
+        if (act && hl == 0) l4_close(F, n, NU);
+        __syncwarp();
+        for (u32 j = hl; j < (act ? NU + 2u : 0u); j += 16) {
             u32 u = 0;
             if (j < NU) {
                 const u32 v = min(8u, n - 8u * j);
                 const int p = (int)n - 8 - 8 * (int)j;                     // the forward window that ends at symbol n - 1 - 8 j (mod n)
-                u = l4_comp8(l4_nibrev(l4_win(F, n, (u32)(p < 0 ? p + (int)n : p))));
+                u = l4_comp8(l4_nibrev(l4_win(F, (u32)(p < 0 ? p + (int)n : p))));
                 if (v < 8u) u &= ~(0xffffffffu >> (4u * v));
             }
             R[j] = u;
         }
         __syncwarp();
-        const u32 U = p4_strand_bytes(n) >> 2;
+        if (act && hl == 0) l4_close(R, n, NU);
+        __syncwarp();
+        const u32 U = act ? p4_strand_bytes(n) >> 2 : 0u;
         u32 *Fo = reinterpret_cast<u32 *>(p4 + p4_byte(off, i)), *Ro = Fo + U;
-        for (u32 j = lane; j < U; j += 32) {
-            u32 q = 8u * j;
+        u32 q = 8u * hl;                                                   // 8 j mod n: 128 symbols per step, n >= 129
+        for (u32 j = hl; j < U; j += 16) {
+            const u32 k = q >> 3, r = 4u * (q & 7u);
+            Fo[j] = __funnelshift_l(F[k + 1], F[k], r);
+            Ro[j] = __funnelshift_l(R[k + 1], R[k], r);
+            q += 128u;
             if (q >= n) q -= n;
-            if (q >= n) q -= n;
-            if (q >= n) q -= n;
-            Fo[j] = l4_win(F, n, q);
-            Ro[j] = l4_win(R, n, q);
         }
-        if (lane == 0) lane_bits[i] = 3;
+        if (act && hl == 0) lane_bits[i] = 3;
         __syncwarp();
     }
 }

@@ -319,7 +319,7 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     if (l4_run) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->timing) { CK_CUDA(ctx, cudaEventCreate(&e0)); CK_CUDA(ctx, cudaEventCreate(&e1)); CK_CUDA(ctx, cudaEventRecord(e0, st)); }
-        k_pack4<<<std::min<u32>((io.n + 7) / 8, 16u * (u32)ctx->num_sms), 256, 0, st>>>(io.bytes, io.offsets, io.lens, const_cast<u8 *>(io.lane), io.n, io.p4);
+        k_pack4<<<std::min<u32>((io.n + 15) / 16, 16u * (u32)ctx->num_sms), 256, 0, st>>>(io.bytes, io.offsets, io.lens, const_cast<u8 *>(io.lane), io.n, io.p4);
         if (ctx->timing) { CK_CUDA(ctx, cudaEventRecord(e1, st)); ctx->ev_pairs[CLS_COUNT + 5].push_back(e0); ctx->ev_pairs[CLS_COUNT + 5].push_back(e1); }
         ctx->launches++;
     }

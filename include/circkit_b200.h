@@ -187,7 +187,11 @@ uint64_t ck_packed2_words(uint64_t total_bytes, uint32_t n_records, uint32_t fla
 int ck_dev_canon_packed2(ck_ctx *ctx, void *stream, const uint64_t *packed2, const uint64_t *offsets,
                          uint32_t n_records, uint32_t flags, uint32_t class_mask, uint8_t *out_bytes, uint32_t *out_start,
                          uint8_t *out_strand, uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
-/* raw/normalised bytes -> lane formats (the k_prepare step), then canonicalise; out_len is required */
+/* raw/normalised bytes -> lane formats (the k_prepare step), then canonicalise; out_len is required.  Records that are not pure
+ * ACGT take the byte-level lanes; of those, records over {-, A, C, G, N, T} -- all that needletail's normalisation
+ * (src/canonicalize.rs:24-27) leaves of IUPAC input -- with 129..2048 symbols and CK_F_ALIGNED_OUT are packed at 4 bits per
+ * symbol, both strands, into a part of the workspace and canonicalised by the lane-per-record kernel of csrc/ck_lane4.cuh;
+ * the host-buffer entries (ck_*_submit*) do the same inside the context. */
 int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const uint64_t *offsets,
                        uint32_t n_records, uint64_t total_bytes, uint32_t flags, uint32_t class_mask,
                        uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start, uint8_t *out_strand,
