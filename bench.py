@@ -50,10 +50,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["mono"])
     ap.add_argument("--records", type=int, default=0, help="override records per GPU (smaller = NOT the named config)")
-    ap.add_argument("--e2e-ascii-every", type=int, default=3,
+    ap.add_argument("--e2e-ascii-every", type=int, default=None,
                     help="e2e: every k-th batch goes to the device as ASCII (ck_*_submit: the DMA engine moves it while the host threads "
                          "pack the other batches, ck_pack2_host + ck_*_submit_packed) -- host packing (~70 GB/s of ASCII on 16 threads) and "
-                         "PCIe (~55 GB/s) work side by side instead of one after the other; 0 = every batch packed on the host")
+                         "PCIe (~55 GB/s) work side by side instead of one after the other; 0 = every batch packed on the host.  Default 3; "
+                         "config 3 (IUPAC records: nothing to gain from 2-bit packing on the host): 1 = every batch as ASCII")
     ap.add_argument("--no-config5", action="store_true", help="default workload only: skip the 100 M-record config-5 sub-record")
     ap.add_argument("--c5-records", type=int, default=100_000_000, help="records of the config-5 sub-record, split over the GPUs")
     ap.add_argument("--overlap", dest="overlap", action="store_true", default=None,
@@ -393,9 +394,10 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
     pack_flags = 1 if raw else 0
     stats = dict(pack_s=0.0, h2d=0)
 
-    every = max(0, args.e2e_ascii_every)
+    sched = dict(every=max(0, args.e2e_ascii_every) if args.e2e_ascii_every is not None else (1 if raw else 3))
 
     def is_ascii(i):
+        every = sched["every"]
         return every > 0 and i % every == every - 1
 
     def pack(i):
@@ -464,6 +466,29 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
 
     e2e_step()                         # warm-up
     sync_all()
+    probe = None
+    if args.e2e_ascii_every is None and not raw:
+        # the share of batches that cross PCIe as ASCII is a property of the host (packer threads vs. DMA engine vs. memory
+        # bandwidth): one untimed step per candidate, the same choice on every rank
+        probe = {}
+        for cand in (3, 2, 1, 4, 6, 0):
+            sched["every"] = cand
+            e2e_step()
+            sync_all()
+            tq = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            dq = time.perf_counter() - tq
+            if world > 1:
+                t = torch.tensor([dq], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dq = float(t.item())
+            probe[cand] = dq
+            sync_all()
+        sched["every"] = min(probe, key=probe.get)
+        e2e_step()
+        sync_all()
+    every = sched["every"]
     t0 = time.perf_counter()
     e2e_steps = max(1, min(steps, 3))
     for _ in range(e2e_steps):
@@ -562,11 +587,17 @@ def e2e_leg(args, ctx, D, torch, dist, dev, rank, world, w, wname, R, resident_f
     d2h = rec_step * ((8 + 8 + 4) if uniq else (4 + 4 + 1))
     e2e = {"value": rec_step / (dt / e2e_steps), "unit": "records/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "batches_per_step": len(batches) if world == 1 else n_batches if rounds * world >= n_batches else rounds * world,
-           "records_per_batch": RB,
-           "api": ("ck_pack2_host + ck_uniq_submit_packed / ck_uniq_wait" if uniq else "ck_pack2_host + ck_canon_submit_packed / ck_canon_wait")
+           "records_per_batch": RB, "ascii_every": every,
+           "ascii_every_probe_seconds": {str(k): round(v, 4) for k, v in probe.items()} if probe else None,
+           "api": (("ck_uniq_submit / ck_uniq_wait" if uniq else "ck_canon_submit / ck_canon_wait") if every == 1 else
+                   "ck_pack2_host + ck_uniq_submit_packed / ck_uniq_wait" if uniq else "ck_pack2_host + ck_canon_submit_packed / ck_canon_wait")
                   + (" over a peer group (ck_peer_export / ck_peer_attach): global first indices" if world > 1 and uniq else ""),
            "input": "ASCII record bytes + offsets in pinned host memory; the host packer (%d threads per rank) runs INSIDE the timed region%s"
-                    % (threads, "; every %d-th batch crosses PCIe as ASCII and is packed on the device instead, so that the DMA engine and the "
+                    % (threads, "; every batch crosses PCIe as ASCII and is normalised / packed on the device (k_prepare): the records of this "
+                                "workload are not 2-bit, there is nothing for the host packer to shrink" if every == 1 and raw else
+                                "; every batch crosses PCIe as ASCII and is packed on the device (the probe before the timed steps found "
+                                "the DMA engine alone faster than any mix with the host packer)" if every == 1 else
+                                "; every %d-th batch crosses PCIe as ASCII and is packed on the device instead, so that the DMA engine and the "
                                 "packer threads work side by side" % every if every else ""),
            "result": "first_index + hash64 + length per record" if uniq else "start + strand + length per record",
            "gbases_per_s": bases_step / (dt / e2e_steps) / 1e9, "records_per_step": rec_step,
