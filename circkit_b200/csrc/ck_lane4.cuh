@@ -3,16 +3,20 @@
 // code to N.  The 2-bit lane cannot hold six symbols and the generic warp-per-record byte-lane kernel (k_canon_warp<4>) spends
 // 957 warp instructions on a 325-symbol record; this is the structure of ck_stream3.cuh at 4 bits per symbol:
 //   * k_pack4   : per record, BOTH strands packed (8 symbols per 32-bit unit, first symbol in the top nibble, codes - A C G N T =
-//                 0..5 in byte order, so integer order == lexicographic order) and DOUBLED, 32-byte aligned -- the reverse
+//                 0..5 in byte order, so integer order == lexicographic order), 32-byte aligned, each CONTINUED circularly past its end by
+//                 at least 72 symbols (every 64-symbol window that starts below n is then linear) -- the reverse
 //                 complement is a string of its own here (a 4-bit complement is a table lookup, not one LOP3 as for 2 bits),
-//                 so the kernel below only ever walks forward, on either strand array, with 256-bit loads and no wrap logic.
+//                 so the kernel below only ever walks forward, on either strand array, with 256-bit loads; the one wrap of the
+//                 emit pass is a reload of octs 0 and 1.  (The first form stored both strands doubled, as ck_stream3.cuh does:
+//                 no wrap at all, but 850 instead of 520 bytes per 325-symbol record made the kernel DRAM-bound.)
 //                 Records with another symbol (library semantics with IUPAC letters) keep lane 4 and the generic kernel;
 //   * scan      : one oct (64 symbols) per iteration and strand; per unit 7 funnel shifts give the eight 8-mer keys (32 bits)
 //                 of its rotations, 4 VIMNMX their minimum; the octs' minima are tracked with their (oct, strand) tag, two
 //                 smallest per lane; the one partial oct of a record is scanned with its positions past n masked;
 //   * locate    : the winning oct is replayed, 64 rotations against the minimal key; a unique hit is the canonical rotation,
 //                 anything else (and every record below 129 symbols, 241 with a hash) goes to the generic kernel's duel path;
-//   * emit      : 64 canonical symbols per round = one XXH3 stripe: 9 units selected from the two octs the lane holds, eight
+//   * emit      : 64 canonical symbols per round = one XXH3 stripe, from circular position (start + 64 s) mod n: 9 units
+//                 selected from the two octs the lane holds, eight
 //                 windows, letters by PRMT in the 8-byte table "-ACGNT" (codes < 8: one lookup per four symbols), the conflict-
 //                 free shared-memory stage of ck_stream3.cuh, 128-bit stores.
 #pragma once
@@ -23,10 +27,12 @@ namespace ck {
 #define CK_L4_WARPS 8u
 #define CK_L4_WARP_BYTES (CK_S3_STAGE + 1024u + 384u)
 
-// byte offset of record i's packed4 region, bytes of one (doubled) strand, size of the whole arena
-__host__ __device__ __forceinline__ u64 p4_byte(u64 off, u64 rec) { return 64 * ((off >> 5) + 5 * rec); }
-__host__ __device__ __forceinline__ u32 p4_strand_bytes(u32 n) { return 32u * (((2u * n + 135u) >> 6) + 1u); }
-__host__ __device__ __forceinline__ u64 p4_bytes_total(u64 total, u64 n_records) { return 64 * ((total >> 5) + 5 * n_records + 5); }
+// byte offset of record i's packed4 region, bytes of one strand, size of the whole arena
+// (a strand = the record once plus its circular continuation by at least 72 symbols: what the partial oct of the scan, an
+// output round that starts below n, and the last XXH3 stripe read past n)
+__host__ __device__ __forceinline__ u64 p4_byte(u64 off, u64 rec) { return 32 * ((off >> 5) + 8 * rec); }
+__host__ __device__ __forceinline__ u32 p4_strand_bytes(u32 n) { return 32u * (((n + 135u) >> 6) + 1u); }
+__host__ __device__ __forceinline__ u64 p4_bytes_total(u64 total, u64 n_records) { return 32 * ((total >> 5) + 8 * n_records + 10); }
 
 // four normalised bytes (first symbol in the low byte) -> their four codes as nibbles, first symbol in the TOP nibble of the
 // 16 bits; `bad` collects the bytes (under `mask`) that are not one of - A C G N T.  (b >> 1) & 7 is a perfect hash of the six
@@ -71,11 +77,11 @@ __device__ __forceinline__ void l4_close(u32 *X, u32 n, u32 NU)
 }
 
 // Half a warp per record of the 4-bit lane with 129 <= n <= 2048 (a 325-symbol record has 41 units: 16 lanes use 85 % of
-// their iterations, 32 lanes 64 %): both strands, doubled; lane_bits[i] becomes 3.
+// their iterations, 32 lanes 64 %): both strands, each continued circularly; lane_bits[i] becomes 3.
 //   A: 8 bytes per lane -> one unit of the forward first copy (shared memory, then continued circularly by two units so that
 //      every window of the circle is one funnel shift), alphabet check;
 //   B: the reverse complement's first copy from it (window of the forward copy, nibbles reversed, complemented);
-//   C: units of the doubled strands = windows of the first copies at 8 j mod n, 64-byte coalesced stores.
+//   C: units of the continued strands = windows of the first copies at 8 j mod n, 64-byte coalesced stores.
 #define CK_P4_UNITS 260u
 __global__ void __launch_bounds__(256) k_pack4(const u8 *bytes, const u64 *offsets, const u32 *lens, u8 *lane_bits, u32 n_records, u8 *p4)
 {
@@ -299,9 +305,11 @@ __global__ void __launch_bounds__(32 * CK_L4_WARPS, 2) k_canon_l4(CanonArgs a, c
             const u32 nchunks = fast ? (nn + 15) >> 4 : 0u;
             const u32 nfull = fast ? (nn - 1) >> 6 : 0u;
             const u32 rounds = __reduce_max_sync(CK_FULL, (nchunks + 3) >> 2);
-            const bool b2 = (pos & 32u) != 0, b1 = (pos & 16u) != 0, b0s = (pos & 8u) != 0;
-            const u32 xs = 4u * (pos & 7u);
-            const u32 olim = fast ? 32u * ((2u * nn + 71u) >> 6) : 32u;     // last oct of the strand array a valid round can need
+            // round s emits the 64 symbols that start at circular position cpos = (pos + 64 s) mod n: a linear window of the
+            // strand array (the continuation past n covers a round that starts below n); the round after the one that reaches n
+            // starts in oct 0 again, with another window phase
+            u32 cpos = pos;
+            const u32 olim = fast ? 32u * ((nn + 135u) >> 6) : 32u;         // last oct of the strand array
             u32 onext = ((pos >> 6) << 5) + 64u;
             Oct R0 = ldg256_here(bs + ((pos >> 6) << 5)), R1 = ldg256_here(bs + ((pos >> 6) << 5) + 32);
             u64 acc0 = CK_P32_3, acc1 = CK_P64_1, acc2 = CK_P64_2, acc3 = CK_P64_3;
@@ -319,8 +327,15 @@ __global__ void __launch_bounds__(32 * CK_L4_WARPS, 2) k_canon_l4(CanonArgs a, c
 #define CK_L4_ROUND(LO, UP)                                                                                          \
             {                                                                                                       \
                 u32 w[8];                                                                                           \
-                l4_windows(LO, UP, b2, b1, b0s, xs, w);                                                             \
-                if (s + 1 < rounds) { LO = ldg256_here(bs + min(onext, olim)); onext += 32u; }                      \
+                l4_windows(LO, UP, (cpos & 32u) != 0, (cpos & 16u) != 0, (cpos & 8u) != 0, 4u * (cpos & 7u), w);    \
+                if (s + 1 < rounds) {                                                                               \
+                    const u32 cn = cpos + 64u;                                                                      \
+                    const bool wrap = fast && cn >= nn;                                                             \
+                    if (wrap) UP = ldg256_here(bs);                 /* the next round's lower oct is oct 0 */       \
+                    LO = ldg256_here(bs + (wrap ? 32u : min(onext, olim)));                                         \
+                    onext = wrap ? 64u : onext + 32u;                                                               \
+                    cpos = wrap ? cn - nn : cn;                                                                     \
+                }                                                                                                   \
                 uint4 v[4];                                                                                         \
                 v[0] = l4_ascii16(w[0], w[1]); v[1] = l4_ascii16(w[2], w[3]);                                       \
                 v[2] = l4_ascii16(w[4], w[5]); v[3] = l4_ascii16(w[6], w[7]);                                       \
@@ -358,8 +373,9 @@ __global__ void __launch_bounds__(32 * CK_L4_WARPS, 2) k_canon_l4(CanonArgs a, c
             }
 #undef CK_L4_ROUND
             if (want_hash) {
-                // last stripe: canonical symbols [n - 64, n) = the strand array at pos + n - 64 (doubled: linear)
-                const u32 q = pos + nn - 64u;
+                // last stripe: canonical symbols [n - 64, n) = the strand array at (pos + n - 64) mod n, linear with the continuation
+                u32 q = pos + nn - 64u;
+                if (q >= nn) q -= nn;
                 const Oct LA = ldg256_here(bs + ((q >> 6) << 5)), LB = ldg256_here(bs + ((q >> 6) << 5) + 32);
                 u32 w[8];
                 l4_windows(LA, LB, (q & 32u) != 0, (q & 16u) != 0, (q & 8u) != 0, 4u * (q & 7u), w);
