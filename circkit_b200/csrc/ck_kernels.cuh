@@ -97,6 +97,7 @@ struct CanonArgs {
     u32 min_n, max_n;       // length range of this launch's class (checked when there is no list)
     u32 *retry;             // lane-per-record kernel: records it leaves to the warp / CTA kernels, appended per class at
     u32 *retry_counts;      // retry[retry_counts[16 + class] + atomicAdd(retry_counts + class, 1)]
+    const u8 *lane_bits;    // optional: only records whose symbol lane is this kernel's BITS (the CLS_HUGE list holds every lane)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -151,6 +152,7 @@ __device__ __forceinline__ void do_record(const CanonArgs &a, u32 rec, u32 *Xf, 
     const u64 off = a.offsets[rec];
     const u32 n = a.lens ? a.lens[rec] : (u32)(a.offsets[rec + 1] - off);
     if (a.list == nullptr && (n < a.min_n || n > a.max_n)) return;   // direct mode: k_classify reported it (uniform)
+    if (a.lane_bits) { const u32 lb = a.lane_bits[rec]; if ((lb == 3u ? 4u : lb) != (u32)BITS) return; }
     RecordIn in;
     in.packed2 = a.packed2 ? a.packed2 + p2_word(off, rec, a.p2_dbl) : nullptr;
     in.bytes = a.bytes ? a.bytes + off : nullptr;

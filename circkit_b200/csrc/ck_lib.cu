@@ -79,6 +79,8 @@ u32 cls_smem_bytes(int c)
 struct ExecScratch {
     u32 *tie[CLS_COUNT] = {};
     u64 *seg = nullptr;                 // k_canon_seg: per-warp partial XXH3 sums
+    u32 *huge_x = nullptr, *huge_tie = nullptr;     // CLS_HUGE: strands staged in global memory + tie scratch, grown on demand
+    u64 huge_x_words = 0, huge_tie_words = 0;
     // the per-class launches that follow the lane kernel are independent of each other (own lists, own scratch): they are
     // forked onto side streams and joined back, so that the small retry / tail launches overlap instead of queueing.  One set
     // per in-flight batch (slot 0, slot 1, the device-resident API), so batches never queue behind each other's forks.
@@ -98,6 +100,7 @@ struct Slot {
     ExecScratch scr;
     bool busy = false, uniq = false;
     u32 dbl = 1;                        // packed2 layout of the batch in flight
+    u64 longest = 0;                    // longest raw record of the batch in flight
     u32 *sel = nullptr; u64 *coff = nullptr;    // CK_F_SURVIVORS: survivor indices / compact offsets of the batch in flight
     u32 n = 0, flags = 0; u64 total = 0;
 };
@@ -221,6 +224,9 @@ void free_scratch(ExecScratch &s)
     }
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.seg) cudaFree(s.seg);
+    if (s.huge_x) cudaFree(s.huge_x);
+    if (s.huge_tie) cudaFree(s.huge_tie);
+    s.huge_x = s.huge_tie = nullptr; s.huge_x_words = s.huge_tie_words = 0;
     s.ev_fork = nullptr; s.seg = nullptr;
 }
 
@@ -278,6 +284,8 @@ struct CanonIO {
     const u64 *packed2; const u8 *bytes; const u64 *offsets; const u32 *lens; const u8 *lane;
     u32 n; u32 mode;
     u32 dbl = 1;                      // packed2 layout of the batch: 1 doubled (ck_stream3 / ck_seg2), 0 single copy (ck_stream2)
+    u64 longest = 0;                  // longest raw record of the batch when the host knows it (host-buffer entries): records beyond
+                                      // the staged-length classes are then processed from global memory instead of being reported
     u8 *p4 = nullptr;                 // optional packed4 arena (ck_lane4.cuh), p4_bytes_total(total, n) bytes: enables k_canon_l4
     u8 *out; u32 *out_start; u8 *out_strand; u64 *out_hash;
     u32 *lists; u64 lists_bytes;      // sort workspace: >= ck_lists_bytes(n)
@@ -451,6 +459,41 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
     }
     for (int c = 0; c < CLS_COUNT; c++)
         if ((joined >> c) & 1u) CK_CUDA(ctx, cudaStreamWaitEvent(st, scr.ev_join[c], 0));
+    // records beyond the staged-length classes (2-bit > 425 984, 4-bit > 212 992, bytes > 106 496 symbols): the CTA kernel with
+    // both strands staged in global memory, a few CTAs, one launch per symbol lane over the CLS_HUGE run of the list
+    if (only < 0 && io.longest > cls_max_n(CLS_C8) && (!class_mask || (class_mask & (1u << CLS_HUGE)))) {
+        const u64 nl = io.longest;
+        const u32 G = (u32)std::max<u64>(1, std::min<u64>(32, (1ull << 30) / (2 * nl + 64)));
+        const u64 xw = (u64)G * 2 * strand_units<8>((u32)nl), tw = (u64)G * tie_scratch_words<8>(nl);
+        if (xw > scr.huge_x_words) {
+            if (scr.huge_x) CK_CUDA(ctx, cudaFree(scr.huge_x));
+            scr.huge_x = nullptr; scr.huge_x_words = 0;
+            CK_CUDA(ctx, cudaMalloc(&scr.huge_x, xw * 4));
+            scr.huge_x_words = xw;
+        }
+        if (tw > scr.huge_tie_words) {
+            if (scr.huge_tie) CK_CUDA(ctx, cudaFree(scr.huge_tie));
+            scr.huge_tie = nullptr; scr.huge_tie_words = 0;
+            CK_CUDA(ctx, cudaMalloc(&scr.huge_tie, tw * 4));
+            scr.huge_tie_words = tw;
+        }
+        CanonArgs a = base_args(CLS_HUGE);
+        a.list = sorted; a.count = io.counts + CLS_HUGE; a.n_direct = 0; a.min_n = 1; a.max_n = 0xffffffffu;
+        a.xglobal = scr.huge_x; a.scratch = scr.huge_tie; a.lane_bits = io.lane;
+        a.smem_units = strand_units<2>((u32)nl); a.scratch_stride = tie_scratch_words<2>(nl);
+        if (nl > cls_max_n(CLS_C2B)) { k_canon_cta<2, true><<<G, 1024, 0, st>>>(a); ctx->launches++; }
+        if (io.lane && nl > cls_max_n(CLS_C4)) {
+            a.smem_units = strand_units<4>((u32)nl); a.scratch_stride = tie_scratch_words<4>(nl);
+            k_canon_cta<4, true><<<G, 1024, 0, st>>>(a);
+            ctx->launches++;
+        }
+        if (io.lane) {
+            a.smem_units = strand_units<8>((u32)nl); a.scratch_stride = tie_scratch_words<8>(nl);
+            k_canon_cta<8, true><<<G, 1024, 0, st>>>(a);
+            ctx->launches++;
+        }
+        CK_CUDA(ctx, cudaMemsetAsync(io.counts + CLS_HUGE, 0, 4, st));      // processed: nothing to report
+    }
     CK_CUDA(ctx, cudaGetLastError());
     return CK_OK;
 }
@@ -549,6 +592,7 @@ int submit_check(ck_ctx *ctx, int slot, const uint64_t *offsets, uint32_t n_reco
     }
     if (longest > (1ull << 30)) return fail(ctx, CK_ERR_TOO_LONG, "record longer than 2^30 symbols");
     s.total = total;
+    s.longest = longest;
     s.dbl = longest > 512 ? 1u : 0u;     // batches of short records: single-copy arena (ck_device.cuh)
     return CK_OK;
 }
@@ -599,7 +643,7 @@ int submit_tail(ck_ctx *ctx, Slot &s, bool lens_given, uint64_t base_index)
     CanonIO io{};
     // without normalisation every byte is a symbol: lengths are the offset differences and the lane-per-record kernel applies
     io.packed2 = s.d_p2; io.bytes = s.d_norm; io.offsets = s.d_off; io.lens = lens_given ? s.d_len : nullptr; io.lane = s.d_lane;
-    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u; io.dbl = s.dbl; io.p4 = s.d_p4;
+    io.n = n_records; io.mode = (flags & CK_F_ALIGNED_OUT) ? 2u : 0u; io.dbl = s.dbl; io.p4 = s.d_p4; io.longest = s.longest;
     io.out = (flags & CK_F_NO_BYTES) ? nullptr : s.d_out;
     io.out_start = s.d_start; io.out_strand = s.d_strand; io.out_hash = s.d_hash;
     io.lists = s.d_lists; io.lists_bytes = lists_bytes_for(ctx->cfg.max_batch_records); io.counts = s.d_counts;
@@ -1086,6 +1130,7 @@ static int lib_batch(ck_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets,
     io.packed2 = (u64 *)(d + o_p2); io.bytes = d + o_norm; io.offsets = (u64 *)(d + o_off); io.lens = (u32 *)(d + o_len); io.lane = d + o_lane;
     io.n = n_records; io.mode = mode; io.out = out_bytes ? d + o_out : nullptr; io.out_start = (u32 *)(d + o_start); io.out_strand = d + o_strand;
     io.out_hash = nullptr; io.lists = (u32 *)(d + o_lists); io.lists_bytes = lists_bytes_for(R); io.counts = (u32 *)(d + o_counts);
+    io.longest = longest;
     rc = run_canon(ctx, st, ctx->lib_scr, io, 0);
     if (rc) return rc;
     CK_CUDA(ctx, cudaMemcpyAsync(h_counts, d + o_counts, 64, cudaMemcpyDeviceToHost, st));

@@ -196,7 +196,9 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
                        uint32_t n_records, uint64_t total_bytes, uint32_t flags, uint32_t class_mask,
                        uint8_t *out_bytes, uint32_t *out_len, uint32_t *out_start, uint8_t *out_strand,
                        uint64_t *out_hash64, void *workspace, uint64_t workspace_bytes);
-/* synchronises `stream`; CK_ERR_TOO_LONG if the last call on `workspace` left records unprocessed */
+/* synchronises `stream`; CK_ERR_TOO_LONG if the last call on `workspace` left records unprocessed (the device-resident entries
+ * stop at the staged-length classes: 2-bit 425 984, 4-bit 212 992, bytes 106 496 symbols; the host-buffer entries and the library
+ * drop-ins process longer records from global memory, up to 2^30 symbols) */
 int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace);
 /* first-occurrence table over device arrays; index == NULL means base_index + i */
 uint64_t ck_dev_table_bytes(uint64_t capacity_keys);

@@ -199,6 +199,34 @@ def test_long_records_cta_shape(ctx):
     _check_batch(ctx, seqs, False, tag="long")
 
 
+def test_records_beyond_the_staged_length_classes(ctx):
+    """The reference has no length limit (lib/src/canonicalize.rs:5-36).  Records beyond the classes whose strands fit shared
+    memory (2-bit > 425 984, 4-bit > 212 992, bytes > 106 496 symbols) are staged in global memory (k_canon_cta<BITS, true>):
+    host-buffer batches (ASCII and host-packed), uniq, and the library drop-ins, every symbol lane, with ties."""
+    rng = np.random.default_rng(77)
+
+    def rnd(n, alpha):
+        return bytes(rng.choice(np.frombuffer(alpha, np.uint8), n).astype(np.uint8))
+    u = rnd(1013, b"ACGT")
+    seqs = [rnd(425985, b"ACGT"), rnd(700001, b"ACGT"), rnd(250000, b"ACGTN"), rnd(120000, b"ACGTacgtn"),
+            (u * 600)[:600000],                       # a cut power: every 1013th rotation ties on the key
+            rnd(300000, b"ACGT") * 2,                 # an exact dimer
+            rnd(1000, b"ACGT"), rnd(300, b"ACGTN"), b"", rnd(425984, b"ACGT")]
+    _check_batch(ctx, seqs, False, tag="huge")
+    arena, off = _batch(seqs)
+    want = oracle.canonicalize_batch(arena, off, normalize=False, threads=8)
+    got = ctx.canonicalize_batch_packed(arena, off, normalize=False)
+    assert np.array_equal(got["hash"], want["hash"]) and np.array_equal(got["start"], want["start"])
+    ctx.uniq_reset()
+    first = ctx.uniq_batch(np.concatenate([arena, arena]), np.concatenate([off, off[1:] + off[-1]]), want_bytes=False)["first"]
+    n = len(seqs)
+    assert [int(x) for x in first[n:]] == [int(x) for x in first[:n]]                # the second copies point at the first ones
+    assert sorted(set(int(x) for x in first[:n])) == [i for i in range(n) if int(first[i]) == i]
+    assert ctx.canonicalize(seqs[1]) == oracle.canonicalize(seqs[1])
+    assert ctx.lmsr_index(seqs[4]) == oracle.lmsr_index(seqs[4])
+    assert ctx.canonicalize(seqs[2]) == oracle.canonicalize(seqs[2])
+
+
 def test_segment_kernel_lengths_and_rotations(ctx):
     """k_canon_seg (one warp per record, a lane per segment): lengths around its oct / block / class boundaries, every record
     also as a rotated and as a reverse-complemented copy (the same canonical form and hash must come back), and records whose
