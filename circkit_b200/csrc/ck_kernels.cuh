@@ -59,17 +59,20 @@ __host__ __device__ constexpr int cls_of_rank(u32 r)
 // 8.21 ms, config 5: 1.92 -> 4.32 ms -- far more than the separate insert pass costs.)
 struct TableSlot { u64 key; u64 first; };
 #define CK_EMPTY_KEY 0xffffffffffffffffULL
-__device__ __forceinline__ u64 table_home(u64 key, u64 mask) { return (key ^ (key >> 29)) & mask; }
+// home slot in a table of any size: the high half of mix(key) * nslots (no power of two needed: 1.5 slots per key instead of
+// 2..4, and the table of a 10 M-key batch is 250 MB instead of 537 MB -- closer to what L2 can hold).  The multiplicative mix
+// spreads keys whose top bits are all alike (the keys a rank owns in the multi-GPU exchange are one range of the top bits).
+__device__ __forceinline__ u64 table_home(u64 key, u64 nslots) { return __umul64hi((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL, nslots); }
 // CAS the key into its probe sequence, keep the minimum index; returns the slot (~0: the side slot of key == EMPTY,
 // ~0 - 1: table full)
-__device__ __forceinline__ u64 table_insert_one(TableSlot *slots, u64 mask, u64 *side_first, u32 *overflow, u64 key, u64 idx)
+__device__ __forceinline__ u64 table_insert_one(TableSlot *slots, u64 nslots, u64 *side_first, u32 *overflow, u64 key, u64 idx)
 {
     if (key == CK_EMPTY_KEY) { atomicMin(side_first, idx); return ~0ULL; }
-    u64 s = table_home(key, mask);
-    for (u64 probes = 0; probes <= mask; probes++) {
+    u64 s = table_home(key, nslots);
+    for (u64 probes = 0; probes < nslots; probes++) {
         const u64 prev = atomicCAS(&slots[s].key, CK_EMPTY_KEY, key);
         if (prev == CK_EMPTY_KEY || prev == key) { atomicMin(&slots[s].first, idx); return s; }
-        s = (s + 1) & mask;
+        s = s + 1 == nslots ? 0 : s + 1;
     }
     *overflow = 1;
     return ~0ULL - 1;
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(256) k_scatter_lane_bytes(const u8 *lane_bytes
 // kept in a side slot, so every u64 stays a legal XXH3 value.  Keeping the MIN input index per key
 // reproduces "first record seen wins" of the serial consumer for any insertion order.
 struct TableArgs {
-    TableSlot *slots; u64 mask;          // capacity - 1 (power of two)
+    TableSlot *slots; u64 nslots;        // slots of the table (any number)
     u64 *side_first;                     // first index of key == EMPTY_KEY
     const u64 *hash; const u64 *index;   // index == null: base_index + i
     u32 stride;                          // elements between consecutive records in hash / index (2: interleaved pairs)
@@ -630,15 +633,15 @@ __global__ void __launch_bounds__(256) k_table_insert(TableArgs a)
     const u64 idx = a.index ? a.index[(size_t)i * a.stride] : a.base_index + i;
     if (idx == ~0ULL) { a.slot_of[i] = ~0ULL - 1; return; }     // padding of a fixed-capacity exchange bucket (k_owner_pad)
     if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); a.slot_of[i] = ~0ULL; return; }
-    u64 s = table_home(key, a.mask);
-    for (u64 probes = 0; probes <= a.mask; probes++) {
+    u64 s = table_home(key, a.nslots);
+    for (u64 probes = 0; probes < a.nslots; probes++) {
         u64 prev = atomicCAS(&a.slots[s].key, CK_EMPTY_KEY, key);
         if (prev == CK_EMPTY_KEY || prev == key) {
             atomicMin(&a.slots[s].first, idx);
             a.slot_of[i] = s;
             return;
         }
-        s = (s + 1) & a.mask;
+        s = s + 1 == a.nslots ? 0 : s + 1;
     }
     *a.overflow = 1; a.slot_of[i] = ~0ULL - 1;
 }
@@ -911,7 +914,7 @@ __global__ void k_peer_barrier(PeerBlockPtrs blocks, u32 world, u32 rank, u32 ba
 // sender can have): insert the pairs of all regions, region s holding counts[s] of them; then answer them into the asking
 // ranks' return regions.
 struct RegionArgs {
-    TableSlot *slots; u64 mask; u64 *side_first; u32 *overflow;
+    TableSlot *slots; u64 nslots; u64 *side_first; u32 *overflow;
     const u64 *recv;        // local receive buffer: world regions of cap (hash, index) pairs
     const u64 *counts;      // counts[s] (low 32 bits) = pairs in region s
     u64 *slot_of;           // world * cap entries
@@ -928,12 +931,12 @@ __global__ void __launch_bounds__(256) k_table_insert_regions(RegionArgs a)
         const ulonglong2 pr = pairs[k];
         const u64 key = pr.x, idx = pr.y;
         if (key == CK_EMPTY_KEY) { atomicMin(a.side_first, idx); slot_of[k] = ~0ULL; continue; }
-        u64 sl = table_home(key, a.mask);
+        u64 sl = table_home(key, a.nslots);
         u64 found = ~0ULL - 1;
-        for (u64 probes = 0; probes <= a.mask; probes++) {
+        for (u64 probes = 0; probes < a.nslots; probes++) {
             const u64 prev = atomicCAS(&a.slots[sl].key, CK_EMPTY_KEY, key);
             if (prev == CK_EMPTY_KEY || prev == key) { atomicMin(&a.slots[sl].first, idx); found = sl; break; }
-            sl = (sl + 1) & a.mask;
+            sl = sl + 1 == a.nslots ? 0 : sl + 1;
         }
         if (found == ~0ULL - 1) *a.overflow = 1;
         slot_of[k] = found;

@@ -501,13 +501,14 @@ int run_canon(ck_ctx *ctx, cudaStream_t st, ExecScratch &scr, const CanonIO &io,
 // k_extend_packed2 runs one warp per record (8 per CTA)
 u32 extend_grid(const ck_ctx *ctx, u32 n_records) { return std::max(1u, std::min<u32>((n_records + 7) / 8, 32u * (u32)ctx->num_sms)); }
 
-u64 pow2_at_least(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
+// slots of a first-occurrence table that is to hold `keys` keys: 1.5 per key (load <= 0.67, linear probing), any number
+u64 table_slots_for(u64 keys) { return std::max<u64>(1024, keys + keys / 2 + 16); }
 
 int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, u32 *overflow,
                  const u64 *hash, const u64 *index, u64 base, u32 n, u64 *slot_of, u32 stride = 1)
 {
     if (!n) return CK_OK;
-    TableArgs t{slots, nslots - 1, side, hash, index, stride, base, n, slot_of, nullptr, overflow};
+    TableArgs t{slots, nslots, side, hash, index, stride, base, n, slot_of, nullptr, overflow};
     k_table_insert<<<(n + 255) / 256, 256, 0, st>>>(t);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
@@ -516,7 +517,7 @@ int table_insert(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64
 int table_first(ck_ctx *ctx, cudaStream_t st, TableSlot *slots, u64 nslots, u64 *side, const u64 *slot_of, u32 n, u64 *first)
 {
     if (!n) return CK_OK;
-    TableArgs t{slots, nslots - 1, side, nullptr, nullptr, 1, 0, n, const_cast<u64 *>(slot_of), first, nullptr};
+    TableArgs t{slots, nslots, side, nullptr, nullptr, 1, 0, n, const_cast<u64 *>(slot_of), first, nullptr};
     k_table_first<<<(n + 255) / 256, 256, 0, st>>>(t);
     ctx->launches++;
     CK_CUDA(ctx, cudaGetLastError());
@@ -554,7 +555,7 @@ int peer_first_index(ck_ctx *ctx, cudaStream_t st, u32 slot, const u64 *hash, u3
         ctx->launches++;
     }
     k_peer_barrier<<<1, 32, 0, st>>>(blocks, P.world, P.rank, 2 * slot, ++P.epoch[2 * slot], P.cursors[slot], slot);
-    ra.slots = table; ra.mask = nslots - 1; ra.side_first = side; ra.overflow = overflow;
+    ra.slots = table; ra.nslots = nslots; ra.side_first = side; ra.overflow = overflow;
     ra.recv = P.recv(P.rank, slot); ra.counts = P.counts(P.rank, slot); ra.slot_of = P.slot_of[slot];
     ra.world = P.world; ra.rank = P.rank; ra.cap = P.cap;
     const u32 gx = std::max<u32>(1u, std::min<u32>((P.cap + 255) / 256, (8u * (u32)ctx->num_sms + P.world - 1) / P.world));
@@ -780,7 +781,7 @@ int wait_common(ck_ctx *ctx, int slot, bool uniq, uint8_t *out_bytes, uint32_t *
 static bool table_view(void *table, u64 bytes, TableSlot *&slots, u64 &nslots, u64 *&side, u32 *&overflow)
 {
     if (!table || bytes < 64 + sizeof(TableSlot) * 16) return false;
-    nslots = 1; while (nslots * 2 * sizeof(TableSlot) + 64 <= bytes) nslots <<= 1;
+    nslots = (bytes - 64) / sizeof(TableSlot);
     side = (u64 *)table; overflow = (u32 *)((u8 *)table + 8);
     slots = (TableSlot *)((u8 *)table + 64);
     return true;
@@ -857,7 +858,7 @@ int ck_init(const ck_config *cfg, ck_ctx **out)
     CK_INIT(cudaMalloc(&ctx->d_overflow, 4));
     CK_INIT(cudaMemset(ctx->d_overflow, 0, 4));
     if (cfg->table_capacity) {
-        ctx->table_slots = pow2_at_least(2 * cfg->table_capacity + 16);
+        ctx->table_slots = table_slots_for(cfg->table_capacity);
         CK_INIT(cudaMalloc(&ctx->table, ctx->table_slots * sizeof(TableSlot)));
         k_table_clear<<<ctx->num_sms * 4, 256>>>(ctx->table, ctx->table_slots, ctx->side);
         CK_INIT(cudaGetLastError());
@@ -1239,7 +1240,7 @@ int ck_dev_check(ck_ctx *ctx, void *stream, const void *workspace)
     return CK_OK;
 }
 
-uint64_t ck_dev_table_bytes(uint64_t capacity_keys) { return pow2_at_least(2 * capacity_keys + 16) * sizeof(TableSlot) + 64; }
+uint64_t ck_dev_table_bytes(uint64_t capacity_keys) { return table_slots_for(capacity_keys) * sizeof(TableSlot) + 64; }
 int ck_dev_table_clear(ck_ctx *ctx, void *stream, void *table, uint64_t table_bytes)
 {
     TableSlot *slots; u64 nslots; u64 *side; u32 *ov;
