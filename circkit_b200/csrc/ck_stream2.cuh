@@ -52,11 +52,73 @@ __device__ __forceinline__ void cp_async16(u32 dst, const void *src)
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// the three smallest (key << 16 | step tag) values: two steps that share the minimal 8-mer can be told apart in the lane
+// (s3_ext16) as long as a third one does not carry it too
+__device__ __forceinline__ void t3_track(u32 &m1, u32 &m2, u32 &m3, u32 v)
+{
+    m3 = min(m3, max(m2, v));
+    m2 = min(m2, max(m1, v));
+    m1 = min(m1, v);
+}
+// the same for the two values of a step (forward, reverse) at once: the three smallest of the merge of (m1 <= m2 <= m3) and
+// (lo <= hi) are min over k of max(m[3 - k], b[k]) -- 8 operations instead of 10
+__device__ __forceinline__ void t3_track2(u32 &m1, u32 &m2, u32 &m3, u32 a, u32 b)
+{
+    const u32 lo = min(a, b), hi = max(a, b);
+    const u32 n3 = __vimin3_u32(m3, max(m2, lo), max(m1, hi));
+    const u32 n2 = __vimin3_u32(m2, max(m1, lo), hi);
+    m1 = min(m1, lo); m2 = n2; m3 = n3;
+}
+// replay step (tag >> 1) of strand (tag & 1): bit s of the result = rotation s of the step carries the 8-mer (m >> 16) and lies below n
+__device__ __forceinline__ u32 s3_replay(const u8 *base, u32 nn, u32 m)
+{
+    const u32 t = (m & 0xffffu) >> 1, strand = m & 1u;
+    const uint2 x01 = ldg64(base + 8 * t);
+    const u32 x2 = ldg32(base + 8 * t + 8);
+    const u32 y0 = strand ? w2_revcomp(x2) : x01.x, y1 = strand ? w2_revcomp(x01.y) : x01.y;
+    const u32 y2 = strand ? w2_revcomp(x01.x) : x2;
+    const u32 bb = (m >> 16) * 0x10001u;
+    u32 nm = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 wa = i ? __funnelshift_l(y1, y0, 2 * i) : y0, wb = i ? __funnelshift_l(y2, y1, 2 * i) : y1;
+        nm += __vminu2(wa ^ bb, 0x00010001u) << i;         // bits 16 + i / i: key i / key 8 + i differs
+        nm += __vminu2(wb ^ bb, 0x00010001u) << (i + 8);   // bits 24 + i / 8 + i: key 16 + i / key 24 + i differs
+    }
+    const u32 match = ~__byte_perm(nm, 0, 0x1302);         // bit s: key s of the step equals the minimum
+    const int lim = (int)nn - 32 * (int)t;
+    const u32 valid = strand ? (lim >= 32 ? 0xffffffffu : 0xffffffffu << (32 - lim))
+                             : (lim >= 32 ? 0xffffffffu : (1u << lim) - 1u);
+    return match & valid;
+}
+// rotation start, in the strand's own coordinates, of hit s of step (tag >> 1) of strand (tag & 1)
+__device__ __forceinline__ u32 s3_start(u32 nn, u32 m, u32 s)
+{
+    const u32 t = (m & 0xffffu) >> 1;
+    int st = (m & 1u) ? (int)nn - 48 - 32 * (int)t + (int)s : 32 * (int)t + (int)s;
+    if (st < 0) st += (int)nn;
+    return (u32)st;
+}
+// bases 8 .. 23 of the rotation that starts at `st` of `strand` (32 bits, first base on top): a linear window of the record in
+// either arena layout (the reads end below n + 24, inside the single-copy layout's extension)
+__device__ __forceinline__ u32 s3_ext16(const u8 *base, u32 nn, u32 strand, u32 st)
+{
+    int f0 = strand ? (int)nn - 24 - (int)st : (int)st + 8;      // forward position of the 16 bases (reverse strand: mirrored)
+    if (f0 < 0) f0 += (int)nn;
+    const u32 w = (u32)f0 >> 4, sh = 2u * ((u32)f0 & 15u);
+    const u32 x = __funnelshift_l(ldg32(base + 4 * w + 4), ldg32(base + 4 * w), sh);
+    return strand ? w2_revcomp(x) : x;
+}
+
 template <int V>
 __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
 {
     extern __shared__ __align__(16) u32 smem[];
     constexpr bool want_hash = (V & CK_W2_HASH) != 0, want_out = (V & CK_W2_OUT) != 0, use_list = (V & CK_W2_LIST) != 0;
+    // two rotations with the minimal 8-mer are told apart in the lane (as in ck_stream3.cuh) in the variants without a hash only:
+    // measured on 325-base records, it takes config 1 (canonicalize) from 0.182 to 0.169 ms per step, but slows the hashing
+    // variants' kernel by 5 % (1.77 -> 1.87 ms on config 5), more than the 1 % of records it keeps from the retry kernel are worth
+    constexpr bool kPair = !want_hash;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 aux = (u32)__cvta_generic_to_shared(smem) + wid * CK_S2_WARP_BYTES;   // output stage
     const u32 offs = aux + CK_T2_AUX_BYTES + 16u * lane;           // + 512 * slot: (offset, end) of this lane's record
@@ -152,7 +214,7 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
         const u32 S1 = ((nn + 31) >> 5) - 1;                       // full steps; step S1 is the padded last one
         const u32 S1max = __reduce_max_sync(CK_FULL, fast ? S1 : 0u);
         const u32 qmax = fast ? (S1 + 1) >> 1 : 0u;                // last quad this lane may read (units <= jn + 3)
-        u32 m1 = 0xffffffffu, m2 = 0xffffffffu;
+        u32 m1 = 0xffffffffu, m2 = 0xffffffffu, m3 = 0xffffffffu;
         const uint2 l01 = make_uint2(HT.x, HT.y);                  // units of the last step, needed after the loop
         const u32 l2 = HT.z;
         {
@@ -170,15 +232,15 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
                     const u32 t = 2 * i;                                                                               \
                     const u32 kf = t2_key_hi(w2_step_min16(Q.x, Q.y, Q.z)), kr = t2_key_hi(w2_step_min16(rqz, rqy, rqx)); \
                     const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;                                                    \
-                    t2_track(m1, m2, kf | tag);                                                                        \
-                    t2_track(m1, m2, kr | (tag + 1));                                                                  \
+                    if (kPair) t3_track2(m1, m2, m3, kf | tag, kr | (tag + 1));                                        \
+                    else { t2_track(m1, m2, kf | tag); t2_track(m1, m2, kr | (tag + 1)); }                             \
                 }                                                                                                      \
                 {                                                                                                      \
                     const u32 t = 2 * i + 1;                                                                           \
                     const u32 kf = t2_key_hi(w2_step_min16(Q.z, Q.w, Q1.x)), kr = t2_key_hi(w2_step_min16(rnx, rqw, rqz)); \
                     const u32 tag = (t < S1) ? 2 * t : 0xffff0000u;                                                    \
-                    t2_track(m1, m2, kf | tag);                                                                        \
-                    t2_track(m1, m2, kr | (tag + 1));                                                                  \
+                    if (kPair) t3_track2(m1, m2, m3, kf | tag, kr | (tag + 1));                                        \
+                    else { t2_track(m1, m2, kf | tag); t2_track(m1, m2, kr | (tag + 1)); }                             \
                 }                                                                                                      \
                 rqx = rnx;                                                                                             \
                 if (++i >= iters) break;                                                                               \
@@ -204,36 +266,31 @@ __global__ void __launch_bounds__(32 * CK_S2_WARPS, 2) k_canon_s2(CanonArgs a)
 #undef CK_T2_PAD
             const u32 kf = t2_key_hi(w2_step_min16(l01.x | pT0, l01.y | pT1, l2 | pT2));
             const u32 kr = t2_key_hi(w2_step_min16(w2_revcomp(l2 & ~pA2), w2_revcomp(l01.y & ~pA1), w2_revcomp(l01.x & ~pA0)));
-            t2_track(m1, m2, kf | (2 * S1));
-            t2_track(m1, m2, kr | (2 * S1 + 1));
+            if (kPair) t3_track2(m1, m2, m3, kf | (2 * S1), kr | (2 * S1 + 1));
+            else { t2_track(m1, m2, kf | (2 * S1)); t2_track(m1, m2, kr | (2 * S1 + 1)); }
         }
-        // ---- locate: replay the winning step, find the rotation that carries the minimal 8-mer
+        // ---- locate: replay the winning step, find the rotation that carries the minimal 8-mer.  Exactly two rotations
+        //      with it (9 % of 3 kb records) are told apart by their next 16 bases; anything else that ties takes the duel path
         {
-            const u32 t = fast ? (m1 & 0xffffu) >> 1 : 0u, strand = m1 & 1u;
-            const uint2 x01 = ldg64(base + 8 * t);
-            const u32 x2 = ldg32(base + 8 * t + 8);
-            const u32 y0 = strand ? w2_revcomp(x2) : x01.x, y1 = strand ? w2_revcomp(x01.y) : x01.y;
-            const u32 y2 = strand ? w2_revcomp(x01.x) : x2;
-            const u32 bb = (m1 >> 16) * 0x10001u;
-            u32 nm = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const u32 wa = i ? __funnelshift_l(y1, y0, 2 * i) : y0, wb = i ? __funnelshift_l(y2, y1, 2 * i) : y1;
-                nm += __vminu2(wa ^ bb, 0x00010001u) << i;         // bits 16 + i / i: key i / key 8 + i differs
-                nm += __vminu2(wb ^ bb, 0x00010001u) << (i + 8);   // bits 24 + i / 8 + i: key 16 + i / key 24 + i differs
+            const u32 mm1 = fast ? m1 : 0u;
+            const bool eq2 = (m1 ^ m2) < 0x10000u, eq3 = !kPair || (m1 ^ m3) < 0x10000u;
+            const u32 hits1 = s3_replay(base, nn, mm1);
+            u32 hits2 = 0;
+            const bool pair = fast && eq2 && !eq3;
+            if (__any_sync(CK_FULL, pair)) hits2 = s3_replay(base, nn, pair ? m2 : mm1);
+            const u32 c1 = __popc(hits1), c2 = pair ? __popc(hits2) : 0u;
+            u32 st = s3_start(nn, mm1, __ffs(hits1) - 1), strand = mm1 & 1u;
+            if (!(c1 == 1 && !eq2)) {
+                if (fast && !eq3 && c1 + c2 == 2 && (!eq2 || pair)) {
+                    // candidate B: the hit of the second step, or the second hit of the same step
+                    const u32 mb = c2 ? m2 : mm1;
+                    const u32 stb = s3_start(nn, mb, c2 ? __ffs(hits2) - 1 : 31u - __clz(hits1)), sb = mb & 1u;
+                    const u32 ea = s3_ext16(base, nn, strand, st), eb = s3_ext16(base, nn, sb, stb);
+                    if (ea == eb) fast = false;
+                    else if (eb < ea) { st = stb; strand = sb; }
+                } else fast = false;                               // three or more, or none valid: the duel path decides
             }
-            const u32 match = ~__byte_perm(nm, 0, 0x1302);         // bit s: key s of the step equals the minimum
-            // forward: key s is rotation 32 t + s, valid below n.  reverse: key s is forward start 32 t + 40 - s,
-            // valid up to n + 8
-            const int lim = (int)nn - 32 * (int)t;
-            const u32 valid = strand ? (lim >= 32 ? 0xffffffffu : 0xffffffffu << (32 - lim))
-                                     : (lim >= 32 ? 0xffffffffu : (1u << lim) - 1u);
-            const u32 hits = match & valid;
-            const u32 s = __ffs(hits) - 1;
-            int st = strand ? (int)nn - 48 - 32 * (int)t + (int)s : 32 * (int)t + (int)s;
-            if (st < 0) st += (int)nn;
-            os = ((u32)st << 1) | strand;
-            if (((m1 ^ m2) < 0x10000u) || __popc(hits) != 1) fast = false;      // equal minima: the duel path decides
+            os = (st << 1) | strand;
             if (!fast) os = 0;                                     // keeps the dummy walk below inside the record
         }
         // ---- canonical ASCII (+ XXH3-64), lane-private; one stripe (4 chunks of 16 bytes) per round.

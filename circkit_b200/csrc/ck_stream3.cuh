@@ -48,63 +48,6 @@ __device__ __forceinline__ void ldg256_if(Oct &o, const void *p, u32 on)
                  : "l"(p), "r"(on));
 }
 
-// the three smallest (key << 16 | step tag) values: two steps that share the minimal 8-mer can be told apart in the lane
-// (s3_ext16) as long as a third one does not carry it too
-__device__ __forceinline__ void t3_track(u32 &m1, u32 &m2, u32 &m3, u32 v)
-{
-    m3 = min(m3, max(m2, v));
-    m2 = min(m2, max(m1, v));
-    m1 = min(m1, v);
-}
-// the same for the two values of a step (forward, reverse) at once: the three smallest of the merge of (m1 <= m2 <= m3) and
-// (lo <= hi) are min over k of max(m[3 - k], b[k]) -- 8 operations instead of 10
-__device__ __forceinline__ void t3_track2(u32 &m1, u32 &m2, u32 &m3, u32 a, u32 b)
-{
-    const u32 lo = min(a, b), hi = max(a, b);
-    const u32 n3 = __vimin3_u32(m3, max(m2, lo), max(m1, hi));
-    const u32 n2 = __vimin3_u32(m2, max(m1, lo), hi);
-    m1 = min(m1, lo); m2 = n2; m3 = n3;
-}
-// replay step (tag >> 1) of strand (tag & 1): bit s of the result = rotation s of the step carries the 8-mer (m >> 16) and lies below n
-__device__ __forceinline__ u32 s3_replay(const u8 *base, u32 nn, u32 m)
-{
-    const u32 t = (m & 0xffffu) >> 1, strand = m & 1u;
-    const uint2 x01 = ldg64(base + 8 * t);
-    const u32 x2 = ldg32(base + 8 * t + 8);
-    const u32 y0 = strand ? w2_revcomp(x2) : x01.x, y1 = strand ? w2_revcomp(x01.y) : x01.y;
-    const u32 y2 = strand ? w2_revcomp(x01.x) : x2;
-    const u32 bb = (m >> 16) * 0x10001u;
-    u32 nm = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const u32 wa = i ? __funnelshift_l(y1, y0, 2 * i) : y0, wb = i ? __funnelshift_l(y2, y1, 2 * i) : y1;
-        nm += __vminu2(wa ^ bb, 0x00010001u) << i;         // bits 16 + i / i: key i / key 8 + i differs
-        nm += __vminu2(wb ^ bb, 0x00010001u) << (i + 8);   // bits 24 + i / 8 + i: key 16 + i / key 24 + i differs
-    }
-    const u32 match = ~__byte_perm(nm, 0, 0x1302);         // bit s: key s of the step equals the minimum
-    const int lim = (int)nn - 32 * (int)t;
-    const u32 valid = strand ? (lim >= 32 ? 0xffffffffu : 0xffffffffu << (32 - lim))
-                             : (lim >= 32 ? 0xffffffffu : (1u << lim) - 1u);
-    return match & valid;
-}
-// rotation start, in the strand's own coordinates, of hit s of step (tag >> 1) of strand (tag & 1)
-__device__ __forceinline__ u32 s3_start(u32 nn, u32 m, u32 s)
-{
-    const u32 t = (m & 0xffffu) >> 1;
-    int st = (m & 1u) ? (int)nn - 48 - 32 * (int)t + (int)s : 32 * (int)t + (int)s;
-    if (st < 0) st += (int)nn;
-    return (u32)st;
-}
-// bases 8 .. 23 of the rotation that starts at `st` of `strand` (32 bits, first base on top), from the doubled record
-__device__ __forceinline__ u32 s3_ext16(const u8 *base, u32 nn, u32 strand, u32 st)
-{
-    int f0 = strand ? (int)nn - 24 - (int)st : (int)st + 8;      // forward position of the 16 bases (reverse strand: mirrored)
-    if (f0 < 0) f0 += (int)nn;
-    const u32 w = (u32)f0 >> 4, sh = 2u * ((u32)f0 & 15u);
-    const u32 x = __funnelshift_l(ldg32(base + 4 * w + 4), ldg32(base + 4 * w), sh);
-    return strand ? w2_revcomp(x) : x;
-}
-
 template <int V>
 __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
 {
