@@ -77,3 +77,14 @@ def test_class_masks_match_the_header():
     assert D.class_mask_for(200, 5000) == (1 << 0) | (1 << 1) | (1 << 10) | (1 << 11)
     assert D.class_mask_for(5000, 200000) == (1 << 11) | (1 << 2) | (1 << 3)
     assert D.class_mask_for(513, 513) == 1 << 1
+
+
+def test_table_sizing_is_one_and_a_half_slots_per_key():
+    """ck_dev_table_bytes: a 64-byte header + 16-byte slots, 1.5 per key (any number, no power-of-two rounding)."""
+    from circkit_b200 import _native as N
+    lib = N.lib()
+    for keys in (0, 1, 1000, 10_500_000 + 1024, 105_000_000):
+        b = int(lib.ck_dev_table_bytes(keys))
+        slots = (b - 64) // 16
+        assert (b - 64) % 16 == 0 and slots >= 1024
+        assert slots >= keys + keys // 2 and slots <= max(1024, keys + keys // 2 + 16)
