@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(32 * CK_S3_WARPS, 2) k_canon_s3(CanonArgs a)
             fetch_head(((u64)oe.y << 32) | oe.x, length_of(oe), rec1);
         }
         const bool in_class = have && (use_list || (n >= a.min_n && n <= a.max_n));
+        // direct mode (a promise of one class, no work list): this kernel is the only one that looks at every record, so it also
+        // reports the records outside the promise (what k_classify does otherwise)
+        if (!use_list && have && !in_class) atomicAdd(a.retry_counts + ((int)CLS_HUGE - 32), 1u);
         bool fast = in_class && n >= (want_hash ? 129u : 128u);
         const u8 *base = arena + 8ull * p2_word(off, rec, 1u);         // this lane's record, doubled
         u8 *dst = want_out ? a.out + out_byte(off, rec) : nullptr;
