@@ -268,15 +268,27 @@ __global__ void __launch_bounds__(32 * CK_L4_WARPS, 2) k_canon_l4(CanonArgs a, c
         const u32 J1max = __reduce_max_sync(CK_FULL, fast ? J1 : 0u);
         u32 m1k = 0xffffffffu, m1t = 0, m2k = 0xffffffffu;
         {
+            // three octs per strand rotate through the roles (current, next, in flight) by unrolling, not by register moves
             Oct FA = ldg256_here(base_f), FB = ldg256_here(base_f + 32), RA = ldg256_here(base_r), RB = ldg256_here(base_r + 32);
-#pragma unroll 1
-            for (u32 j = 0; j < J1max; j++) {
-                const u32 jn = min(j + 2, J1 + 1);
-                const Oct FN = ldg256_here(base_f + 32 * jn), RN = ldg256_here(base_r + 32 * jn);
-                const u32 kf = l4_oct_min(FA, FB.lo.x), kr = l4_oct_min(RA, RB.lo.x);
-                if (j < J1) { seg_track(m1k, m1t, m2k, kf, 2 * j); seg_track(m1k, m1t, m2k, kr, 2 * j + 1); }
-                FA = FB; FB = FN; RA = RB; RB = RN;
+            Oct FC, RC;
+#define CK_L4_SCAN(A0, A1, A2, B0, B1, B2)                                                                           \
+            {                                                                                                       \
+                const u32 jn = min(j + 2, J1 + 1);                                                                  \
+                A2 = ldg256_here(base_f + 32 * jn); B2 = ldg256_here(base_r + 32 * jn);                             \
+                const u32 kf = l4_oct_min(A0, A1.lo.x), kr = l4_oct_min(B0, B1.lo.x);                               \
+                if (j < J1) { seg_track(m1k, m1t, m2k, kf, 2 * j); seg_track(m1k, m1t, m2k, kr, 2 * j + 1); }       \
+                if (++j >= J1max) break;                                                                            \
             }
+            if (J1max) {
+                u32 j = 0;
+#pragma unroll 1
+                for (;;) {
+                    CK_L4_SCAN(FA, FB, FC, RA, RB, RC)
+                    CK_L4_SCAN(FB, FC, FA, RB, RC, RA)
+                    CK_L4_SCAN(FC, FA, FB, RC, RA, RB)
+                }
+            }
+#undef CK_L4_SCAN
         }
         if (lim) {      // the partial oct: rotations 64 J1 .. n - 1
             const Oct F0 = ldg256_here(base_f + 32 * J1), R0 = ldg256_here(base_r + 32 * J1);
