@@ -958,6 +958,10 @@ def b200_arm(args, wname, R, rank, local_rank, world, dev, steps, warmup, want_e
                 "frac_of_nominal_8TBs": achieved / 8000.0, "class_kernel_ms_per_step": kernel_share,
                 "step_ms": ms_per_step}
 
+    if w.get("raw"):
+        roofline["note"] = ("the layout passes in front of this kernel -- k_prepare (normalise + classify + pack) and k_pack4 (4-bit strands) -- "
+                            "are timed in class_kernel_ms_per_step as 'prepare' and 'pack4': each of them takes longer than the "
+                            "canonicalisation kernel the roofline is quoted for")
     # ---------------- e2e through the host-buffer C ABI (pinned host memory, copies timed)
     e2e = None
     if want_e2e:

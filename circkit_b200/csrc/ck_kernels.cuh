@@ -565,43 +565,61 @@ __global__ void k_list_starts(u32 *counts)
 // One warp per record, one lane per destination unit; every source is a unit of the first copy (in place, unit jn is read
 // while another lane completes it: the bits a reader uses are the same before and after).
 __device__ __forceinline__ u32 p2_last_unit(u32 n) { return max((2u * n + 143u) >> 4, (n >> 4) + 5u); }
+__device__ __forceinline__ void extend_one(u64 *packed2, const u64 *offsets, const u32 *lens, u32 i, const u64 *dense, u32 dbl, u32 lane)
+{
+    const u64 off = offsets[i];
+    const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
+    if (n == 0) return;
+    u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i, dbl));
+    const u32 *S = dense ? reinterpret_cast<const u32 *>(dense + (off >> 5) + i) : U;
+    const u32 jn = n >> 4, last = dbl ? p2_last_unit(n) : jn + 4;          // single copy: the circular extension only
+    if (n >= 80) {
+        for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
+            const u32 r = (16u * j) % n;                          // first base of the unit, modulo n
+            const u32 q = r >> 4, sh = 2u * (r & 15u);
+            u32 w = __funnelshift_l(__ldcg(S + q + 1), __ldcg(S + q), sh);
+            if (r + 16u > n) {                                    // the seam: k bases of the tail, then the head
+                const u32 k = n - r;
+                w = (w & ~(0xffffffffu >> (2u * k))) | (__ldcg(S) >> (2u * k));
+            }
+            U[j] = w;
+        }
+    } else {
+        // tiny records: base by base (at most 20 units)
+        for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
+            u32 v = 0;
+            for (u32 b = 0; b < 16; b++) {
+                const u32 t = (16 * j + b) % n;
+                v = (v << 2) | ((__ldcg(S + (t >> 4)) >> (30 - 2 * (t & 15))) & 3u);
+            }
+            __syncwarp(__activemask());
+            U[j] = v;
+        }
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(256) k_extend_packed2(u64 *packed2, const u64 *offsets, const u32 *lens, const u8 *lane_bits, u32 n_records,
                                                         const u64 *dense, u32 dbl)
 {
     const u32 lane = lane_id();
     const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (u32 i = gw; i < n_records; i += nw) {
-        if (lane_bits && lane_bits[i] != 2) continue;
-        const u64 off = offsets[i];
-        const u32 n = lens ? lens[i] : (u32)(offsets[i + 1] - off);
-        if (n == 0) continue;
-        u32 *U = reinterpret_cast<u32 *>(packed2 + p2_word(off, i, dbl));
-        const u32 *S = dense ? reinterpret_cast<const u32 *>(dense + (off >> 5) + i) : U;
-        const u32 jn = n >> 4, last = dbl ? p2_last_unit(n) : jn + 4;          // single copy: the circular extension only
-        if (n >= 80) {
-            for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
-                const u32 r = (16u * j) % n;                          // first base of the unit, modulo n
-                const u32 q = r >> 4, sh = 2u * (r & 15u);
-                u32 w = __funnelshift_l(__ldcg(S + q + 1), __ldcg(S + q), sh);
-                if (r + 16u > n) {                                    // the seam: k bases of the tail, then the head
-                    const u32 k = n - r;
-                    w = (w & ~(0xffffffffu >> (2u * k))) | (__ldcg(S) >> (2u * k));
-                }
-                U[j] = w;
-            }
-        } else {
-            // tiny records: base by base (at most 20 units)
-            for (u32 j = (dense ? 0u : jn) + lane; j <= last; j += 32) {
-                u32 v = 0;
-                for (u32 b = 0; b < 16; b++) {
-                    const u32 t = (16 * j + b) % n;
-                    v = (v << 2) | ((__ldcg(S + (t >> 4)) >> (30 - 2 * (t & 15))) & 3u);
-                }
-                __syncwarp(__activemask());
-                U[j] = v;
-            }
+    if (n_records < 65536u) {                                     // small batches: a warp per record, all of them at once
+        for (u32 i = gw; i < n_records; i += nw) {
+            if (lane_bits && lane_bits[i] != 2) continue;
+            extend_one(packed2, offsets, lens, i, dense, dbl, lane);
         }
-        __syncwarp();
+        return;
+    }
+    // large batches: a warp looks at the lane tags of 32 records at once, so that a batch without 2-bit records (config 3:
+    // 5 M IUPAC records) costs 32 times fewer dependent loads (0.2 ms -> 10 us)
+    for (u32 i0 = 32u * gw; i0 < n_records; i0 += 32u * nw) {
+        const u32 ii = i0 + lane;
+        u32 m = __ballot_sync(CK_FULL, ii < n_records && (!lane_bits || lane_bits[ii] == 2));
+        while (m) {
+            const u32 i = i0 + (u32)__ffs(m) - 1u;
+            m &= m - 1u;
+            extend_one(packed2, offsets, lens, i, dense, dbl, lane);
+        }
     }
 }
 

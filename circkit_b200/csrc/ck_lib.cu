@@ -145,7 +145,7 @@ struct ck_ctx {
     int lane_kernel = 3;                // 2: ck_stream2.cuh (CK_LANE_KERNEL=2), else ck_stream3.cuh
     // optional per-class kernel timing (bench.py's roofline): event pairs around each class launch
     bool timing = false;
-    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 6];     // [CLS_COUNT] = lane kernel, table insert, table first, segment kernel, 4-bit lane kernel, k_pack4
+    std::vector<cudaEvent_t> ev_pairs[CLS_COUNT + 7];     // [CLS_COUNT] = lane kernel, table insert, table first, segment kernel, 4-bit lane kernel, k_pack4, k_prepare + k_extend_packed2 (device-resident entry)
 };
 
 namespace {
@@ -1226,8 +1226,11 @@ int ck_dev_canon_bytes(ck_ctx *ctx, void *stream, const uint8_t *bytes, const ui
     u8 *p4 = w;
     cudaStream_t st = (cudaStream_t)stream;
     PrepareArgs pa{bytes, U(offsets), n_records, (flags & CK_F_NORMALIZE) | (1u << 2), p2, norm, out_len, lane};
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (ctx->timing) { CK_CUDA(ctx, cudaEventCreate(&pe0)); CK_CUDA(ctx, cudaEventCreate(&pe1)); CK_CUDA(ctx, cudaEventRecord(pe0, st)); }
     k_prepare<<<ctx->num_sms * 32, 256, 0, st>>>(pa);
     k_extend_packed2<<<extend_grid(ctx, n_records), 256, 0, st>>>(p2, U(offsets), out_len, lane, n_records, nullptr, 1u);
+    if (ctx->timing) { CK_CUDA(ctx, cudaEventRecord(pe1, st)); ctx->ev_pairs[CLS_COUNT + 6].push_back(pe0); ctx->ev_pairs[CLS_COUNT + 6].push_back(pe1); }
     ctx->launches += 2;
     CanonIO io{};
     io.packed2 = p2; io.bytes = norm; io.offsets = U(offsets); io.lens = out_len; io.lane = lane; io.n = n_records; io.p4 = p4;
@@ -1411,7 +1414,7 @@ int ck_kernel_times(ck_ctx *ctx, double *out_ms, uint32_t *out_launches, uint32_
     if (!ctx || !out_ms || !out_launches) return ctx ? fail(ctx, CK_ERR_ARG, "null argument") : CK_ERR_ARG;
     CK_CUDA(ctx, cudaDeviceSynchronize());
     for (u32 c = 0; c < n_classes; c++) { out_ms[c] = 0; out_launches[c] = 0; }
-    for (u32 c = 0; c < (u32)CLS_COUNT + 6; c++) {
+    for (u32 c = 0; c < (u32)CLS_COUNT + 7; c++) {
         std::vector<cudaEvent_t> &v = ctx->ev_pairs[c];
         for (size_t k = 0; k + 1 < v.size(); k += 2) {
             float ms = 0;

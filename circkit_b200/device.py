@@ -14,7 +14,7 @@ from .core import Context
 
 CLASS_NAMES = ["2bit_le_512", "2bit_le_2048", "2bit_le_65536", "2bit_le_425984", "4bit_le_2048", "4bit_le_212992",
                "byte_le_1024", "byte_le_106496", "huge", "empty", "2bit_le_4096", "2bit_le_8192", "2bit_lane_128_8192",
-               "table_insert", "table_first", "2bit_seg_8193_425984", "4bit_lane_129_2048", "pack4"]
+               "table_insert", "table_first", "2bit_seg_8193_425984", "4bit_lane_129_2048", "pack4", "prepare"]
 # length range [lo, hi] of each 2-bit class (class_mask bit = index in CLASS_NAMES)
 BYTE_CLASSES = ("4bit_le_2048", "4bit_le_212992", "byte_le_1024", "byte_le_106496")
 CLASS_RANGE = {"2bit_le_512": (1, 512), "2bit_le_2048": (513, 2048), "2bit_le_4096": (2049, 4096), "2bit_le_8192": (4097, 8192),
